@@ -237,6 +237,7 @@ typedef struct {
     REAL xn[NX];     /* state leaving the step (normalised) */
     REAL rn;         /* 1/|q~|                               */
     REAL sig[6];     /* diffusion                            */
+    REAL dsg[6];     /* sig0 * sigmoid(s): d sig / d s       */
     REAL disc;       /* gamma^t                              */
     OTAPE mlp;
 } CAT(ostep_, SUFFIX);
@@ -277,6 +278,7 @@ static REAL FN(step_fwd)(const sdempc_config* c, const OMODEL* m, OSTEP* st, con
     REAL sig2 = 0;
     for (int i = 0; i < 6; ++i) {
         st->sig[i] = m->sig0[i] * M_SOFTPLUS(tp->out[1][i]);
+        st->dsg[i] = m->sig0[i] * M_SIGMOID(tp->out[1][i]);
         sig2 = (i == 0) ? st->sig[0] * st->sig[0] : FMA(st->sig[i], st->sig[i], sig2);
     }
     REAL* xn = st->xn;
@@ -375,7 +377,7 @@ static void FN(step_bwd)(const sdempc_config* c, const OMODEL* m, const OSTEP* s
     for (int j = 0; j < 3; ++j) lfb[j] = FMA(R[2][j], la[2], FMA(R[1][j], la[1], R[0][j] * la[0]));
     REAL lout[2][6];
     for (int k = 0; k < 3; ++k) { lout[0][k] = lfb[k]; lout[0][3 + k] = m->J[k] * lMb[k]; }
-    for (int i = 0; i < 6; ++i) lout[1][i] = (lsig[i] * m->sig0[i]) * M_SIGMOID(st->mlp.out[1][i]);
+    for (int i = 0; i < 6; ++i) lout[1][i] = lsig[i] * st->dsg[i];
     const REAL lTsum = -(lfb[2] * m->inv_m);
     for (int i = 0; i < nu; ++i) {
         const REAL lT = FMA(m->mixer[2][i], lMb[2], FMA(m->mixer[1][i], lMb[1], FMA(m->mixer[0][i], lMb[0], lTsum)));

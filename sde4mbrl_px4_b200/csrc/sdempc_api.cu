@@ -1,0 +1,922 @@
+// sdempc_api.cu — __global__ entry points and the C ABI of include/sdempc.h.
+//
+// Build (see __graft_entry__.build()):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 \
+//        -shared -Xcompiler -fPIC -cudart static sdempc_api.cu -o ../libsdempc.so
+// -fmad=false is REQUIRED: every fused multiply-add of SPEC-ARITH is written
+// explicitly (__fmaf_rn / __ffma2_rn); nothing else may be contracted.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mpc_kernels.cuh"
+
+using namespace sdempc;
+
+// =====================================================================================
+// device entry points
+// =====================================================================================
+enum { MODE_SOLVE = 0, MODE_ROLLOUT = 1, MODE_CLOSED_LOOP = 2 };
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+// Team-level epilogue shared by solve and rollout: mean trajectory -> external frame -> global
+template <int NU, int W, int PP>
+__device__ __forceinline__ void write_x_evol(const KParams& P, const Team<PP>& tm, Warp<NU, W>& c, float* dst) {
+    tm.sync();   // all particles' state tapes complete
+    if (tm.warp_in_team == 0 && dst != nullptr) {
+        const int t = c.lane;
+        if (t <= P.H) {
+            const float invP = __fdiv_rn(1.0f, (float)PP);
+            float row[NX], o[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) row[i] = tm.warp0_base[P.o_xtape + t * 16 + i];
+#pragma unroll
+            for (int p = 1; p < PP; ++p)
+#pragma unroll
+                for (int i = 0; i < NX; ++i) row[i] = row[i] + tm.warp0_base[p * tm.ws_stride + P.o_xtape + t * 16 + i];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) row[i] = row[i] * invP;
+            quat_renorm(row + 6);
+            if (P.flags & SDEMPC_F_FRAME_ENU) enu_ned(row, o);
+            else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) o[i] = row[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) dst[t * NX + i] = o[i];
+        }
+    }
+    tm.sync();   // tapes may be overwritten by the next problem
+}
+
+template <int NU, int W, int PP, int G, int MODE>
+__global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
+    using L = Layout<NU, W>;
+    extern __shared__ __align__(128) float smem[];
+    float* ws = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::SMEM_FLOATS);
+    float* team_base = smem + L::SMEM_FLOATS + 4;
+    float* warp_base = team_base + G * P.team_stride;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team = warp / PP, wit = warp % PP;
+
+    // ---- stage the weight image once per CTA: TMA bulk copy + mbarrier ----
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        constexpr uint32_t bytes = L::SMEM_FLOATS * 4;
+        mbar_expect_tx(bar, bytes);
+        constexpr uint32_t CH = 32768;   // keep each bulk request modest
+        for (uint32_t off = 0; off < bytes; off += CH)
+            tma_bulk_g2s(reinterpret_cast<char*>(ws) + off, reinterpret_cast<const char*>(P.wimg) + off,
+                         (bytes - off) < CH ? (bytes - off) : CH, bar);
+    }
+
+    Warp<NU, W> c;
+    c.lane = lane;
+    c.ws = ws;
+    float* wb = warp_base + (size_t)warp * P.ws_stride;
+    c.xk = wb + P.o_xk; c.yk = wb + P.o_yk; c.g = wb + P.o_g; c.xp = wb + P.o_xp; c.uprev = wb + P.o_uprev;
+    c.xref = wb + P.o_xref; c.xi = wb + P.o_xi; c.xtape = wb + P.o_xtape; c.stape = wb + P.o_stape;
+    c.bufA = wb + P.o_bufA; c.bufB = wb + P.o_bufB; c.act3 = wb + P.o_act3; c.lz = wb + P.o_lz; c.red = wb + P.o_red;
+    if (P.mtape_g != nullptr)
+        c.mtape = P.mtape_g + ((size_t)blockIdx.x * (G * PP) + warp) * (size_t)P.H * 2 * W;
+    else
+        c.mtape = reinterpret_cast<float2*>(wb + P.o_mtape);
+    c.load_regs(P.wimg);
+
+    Team<PP> tm;
+    tm.warp_in_team = wit;
+    tm.bar_id = 1 + team;
+    tm.scratch = team_base + team * P.team_stride;
+    tm.warp0_base = warp_base + (size_t)(team * PP) * P.ws_stride;
+    tm.ws_stride = P.ws_stride;
+
+    mbar_wait(bar, 0);
+
+    const int n = P.H * NU;
+    const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
+
+    for (int b = blockIdx.x * G + team; b < P.B; b += gridDim.x * G) {
+        // ---- state ----
+        float x0[NX];
+        {
+            const float* xs = P.x + (size_t)b * NX;
+            float tmp[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) tmp[i] = __ldg(xs + i);
+            if (enu) enu_ned(tmp, x0);
+            else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) x0[i] = tmp[i];
+            }
+        }
+        if constexpr (MODE != MODE_CLOSED_LOOP) {
+            build_window<NU, W>(P, c, P.xref_win ? P.xref_win + (size_t)b * (P.H + 1) * NX : nullptr,
+                                P.curr_t ? P.curr_t + b : nullptr, P.xdes ? P.xdes + (size_t)b * NX : nullptr, 0.f, false);
+            if (P.xi_override != nullptr) {
+                if (lane < P.H) {
+                    const float* src = P.xi_override + (((size_t)b * PP + wit) * P.H + lane) * 6;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) c.xi[lane * 8 + i] = __ldg(src + i);
+                }
+            } else {
+                gen_noise<NU, W>(P, c, P.rng[2 * (size_t)b], P.rng[2 * (size_t)b + 1], (uint32_t)wit, 0u, P.H, c.xi);
+            }
+        }
+
+        if constexpr (MODE == MODE_SOLVE) {
+            const float* pin = P.u_plan + (size_t)b * n;   // staged input plan (never written by the kernel)
+            if (lane < NU) c.uprev[lane] = __ldg(pin + lane);
+            for (int i = lane; i < n; i += 32) {
+                const int t = i / NU, ii = i % NU;
+                const int ts = (P.flags & SDEMPC_F_NO_SHIFT) ? t : (t + 1 < P.H ? t + 1 : P.H - 1);
+                c.xk[i] = clipf(__ldg(pin + ts * NU + ii), P.u_lo[ii], P.u_hi[ii]);
+            }
+            __syncwarp();
+            float s = P.info[b].stepsize;
+            s = s > 0.f ? s : P.init_step;
+            sdempc_info inf;
+            apg_solve<NU, W, PP>(P, c, tm, x0, s, inf, P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
+            float* pout = P.u_plan_out + (size_t)b * n;
+            if (wit == 0) {
+                for (int i = lane; i < n; i += 32) pout[i] = c.xk[i];
+                if (lane == 0) P.info_out[b] = inf;
+            }
+            write_x_evol<NU, W, PP>(P, tm, c, P.x_evol + (size_t)b * (P.H + 1) * NX);
+        } else if constexpr (MODE == MODE_ROLLOUT) {
+            const float* uin = P.u_in + (size_t)b * n;
+            if (lane < NU) c.uprev[lane] = __ldg(P.uprev_in + (size_t)b * NU + lane);
+            for (int i = lane; i < n; i += 32) c.xk[i] = __ldg(uin + i);
+            __syncwarp();
+            const float invP = __fdiv_rn(1.0f, (float)PP);
+            const float Jw = rollout_fwd<NU, W, 1>(P, c, c.xk, x0);
+            if (P.grad_out != nullptr) rollout_bwd<NU, W>(P, c, c.xk);
+            const float J = team_mean_cost<PP>(tm, Jw, lane, invP);
+            if (P.grad_out != nullptr) {
+                team_mean_grad<NU, W, PP>(P, tm, c, n, invP);
+                if (wit == 0)
+                    for (int i = lane; i < n; i += 32) P.grad_out[(size_t)b * n + i] = c.g[i];
+            }
+            if (wit == 0 && lane == 0) P.cost_out[b] = J;
+            write_x_evol<NU, W, PP>(P, tm, c, P.x_evol ? P.x_evol + (size_t)b * (P.H + 1) * NX : nullptr);
+        } else {
+            // ---- Monte-Carlo closed loop: `ticks` x (solve -> plant step) on device ----
+            const unsigned long long seed = P.rng[2 * (size_t)b];
+            unsigned long long tick = P.rng[2 * (size_t)b + 1];
+            const float t0 = __ldg(P.t0 + b);
+            for (int i = lane; i < n; i += 32) { const int ii = i % NU; c.xk[i] = clipf(P.uref[ii], P.u_lo[ii], P.u_hi[ii]); }
+            __syncwarp();
+            float s = P.init_step;
+            float se = 0.f, me = 0.f, sc = 0.f, sn = 0.f;
+            const float dt0 = P.dt[0];
+            for (int k = 0; k < P.ticks; ++k, ++tick) {
+                if (P.x_hist != nullptr && wit == 0 && lane == 0) {
+                    float o[NX];
+                    if (enu) enu_ned(x0, o);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < NX; ++i) o[i] = x0[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) P.x_hist[((size_t)b * (P.ticks + 1) + k) * NX + i] = o[i];
+                }
+                build_window<NU, W>(P, c, nullptr, nullptr, nullptr, fma_((float)k, dt0, t0), true);
+                gen_noise<NU, W>(P, c, seed, tick, (uint32_t)wit, 0u, P.H, c.xi);
+                // warm start: uprev = plan[0], shift
+                float keep[(SDEMPC_MAX_H * SDEMPC_MAX_NU + 31) / 32];
+                {
+                    int m = 0;
+                    for (int i = lane; i < n; i += 32, ++m) {
+                        const int t = i / NU, ii = i % NU;
+                        const int ts = (P.flags & SDEMPC_F_NO_SHIFT) ? t : (t + 1 < P.H ? t + 1 : P.H - 1);
+                        keep[m] = clipf(c.xk[ts * NU + ii], P.u_lo[ii], P.u_hi[ii]);
+                    }
+                    if (lane < NU) c.uprev[lane] = c.xk[lane];
+                    __syncwarp();
+                    m = 0;
+                    for (int i = lane; i < n; i += 32, ++m) c.xk[i] = keep[m];
+                    __syncwarp();
+                }
+                sdempc_info inf;
+                apg_solve<NU, W, PP>(P, c, tm, x0, s, inf, nullptr);
+                s = inf.stepsize;
+                sc = sc + inf.opt_cost;
+                sn = sn + inf.num_steps;
+                float u0[NU];
+                load_u<NU>(c.xk, 0, u0);
+                if (P.u_hist != nullptr && wit == 0 && lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) P.u_hist[((size_t)b * P.ticks + k) * NU + i] = u0[i];
+                }
+                // plant step: same SDE, one particle, Philox sub-stream 2 (every warp of the team
+                // integrates the same plant state redundantly)
+                tm.sync();
+                gen_noise<NU, W>(P, c, seed, tick, 0u, 2u, 1, c.xi);
+                __syncwarp();
+                (void)fwd_step<NU, W, 0>(P, c, 0, 1.f, x0, u0, u0);
+                __syncwarp();
+                float e2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { const float d = x0[i] - c.xref[16 + i]; e2 = fma_(d, d, e2); }
+                se = se + e2;
+                me = e2 > me ? e2 : me;
+            }
+            if (wit == 0 && lane == 0) {
+                if (P.x_hist != nullptr) {
+                    float o[NX];
+                    if (enu) enu_ned(x0, o);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < NX; ++i) o[i] = x0[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) P.x_hist[((size_t)b * (P.ticks + 1) + P.ticks) * NX + i] = o[i];
+                }
+                const float tk = (float)P.ticks;
+                P.stats[(size_t)b * 4 + 0] = __fsqrt_rn(__fdiv_rn(se, tk));
+                P.stats[(size_t)b * 4 + 1] = __fsqrt_rn(me);
+                P.stats[(size_t)b * 4 + 2] = __fdiv_rn(sc, tk);
+                P.stats[(size_t)b * 4 + 3] = __fdiv_rn(sn, tk);
+            }
+            tm.sync();
+        }
+    }
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) return fail(SDEMPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct KernelChoice {
+    void (*solve)(KParams);
+    void (*rollout)(KParams);
+    void (*closed)(KParams);
+    int nu, W, P, G;
+    int wimg_floats, wsmem_floats;
+    bool wreg;
+};
+
+template <int NU, int W, int PP, int G>
+static KernelChoice make_choice() {
+    using L = Layout<NU, W>;
+    KernelChoice k;
+    k.solve = mpc_kernel<NU, W, PP, G, MODE_SOLVE>;
+    k.rollout = mpc_kernel<NU, W, PP, G, MODE_ROLLOUT>;
+    k.closed = mpc_kernel<NU, W, PP, G, MODE_CLOSED_LOOP>;
+    k.nu = NU; k.W = W; k.P = PP; k.G = G;
+    k.wimg_floats = L::TOTAL; k.wsmem_floats = L::SMEM_FLOATS; k.wreg = L::WREG;
+    return k;
+}
+
+// Compiled (nu, width, particles, teams-per-CTA) combinations.
+static const std::vector<KernelChoice>& choices() {
+    static const std::vector<KernelChoice> v = {
+        make_choice<4, 32, 1, 8>(), make_choice<4, 32, 2, 4>(), make_choice<4, 32, 4, 2>(), make_choice<4, 32, 8, 1>(),
+        make_choice<6, 32, 1, 8>(), make_choice<6, 32, 8, 1>(),
+        make_choice<4, 64, 1, 8>(), make_choice<6, 64, 1, 8>(), make_choice<6, 64, 8, 1>(),
+    };
+    return v;
+}
+
+struct sdempc_handle {
+    sdempc_config cfg;
+    sdempc_model_header mh;
+    std::vector<float> weights;       // raw blob payload
+    std::vector<float> wimg;          // packed image
+    std::vector<float> traj_ext, traj_int;
+    int T = 0;
+    int device = 0;
+    KernelChoice kc;
+    KParams kp;                       // template (config + model + layout)
+    size_t smem_bytes = 0;
+    // lazily created device state
+    bool dev_ready = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float* d_wimg = nullptr;
+    float* d_traj = nullptr;
+    float2* d_mtape = nullptr;
+    size_t mtape_warps = 0;
+    char* d_in = nullptr; char* h_in = nullptr; size_t in_cap = 0;
+    char* d_out = nullptr; char* h_out = nullptr; size_t out_cap = 0;
+    float* d_trace = nullptr; size_t trace_cap = 0;
+    char* d_flush = nullptr;
+    int sm_count = 0;
+    int64_t launches = 0;
+    int last_grid = 0;
+    int regs = 0;
+    // staged launch
+    KParams staged;
+    int staged_B = 0;
+    bool staged_ok = false;
+    float last_ms = 0.f;
+};
+
+static void pack_weights(sdempc_handle* h) {
+    const int NU = h->mh.nu, W = h->mh.width, NIN = 6 + NU;
+    const int PAIR = 2 * W + 4;
+    const int W2T = 0, W1T = W2T + W * PAIR, W3RS = W + 4, W3R = W1T + NIN * PAIR, B3 = W3R + 12 * W3RS, PART_A = B3 + 16;
+    const int W1PS = (2 * NIN) % 8 == 4 ? 2 * NIN : 2 * NIN + 4;
+    const int W1P = PART_A, W2P = W1P + W * W1PS, W3C = W2P + W * PAIR, B1 = W3C + W * 12, B2 = B1 + 2 * W, TOTAL = B2 + 2 * W;
+    h->wimg.assign(TOTAL, 0.f);
+    const float* p = h->weights.data();
+    const float *W1[2], *b1[2], *W2[2], *b2[2], *W3[2], *b3[2];
+    for (int n = 0; n < 2; ++n) {
+        W1[n] = p; p += (size_t)W * NIN;
+        b1[n] = p; p += W;
+        W2[n] = p; p += (size_t)W * W;
+        b2[n] = p; p += W;
+        W3[n] = p; p += 6 * (size_t)W;
+        b3[n] = p; p += 6;
+    }
+    float* I = h->wimg.data();
+    for (int n = 0; n < 2; ++n) {
+        for (int k = 0; k < W; ++k)
+            for (int j = 0; j < W; ++j) I[W2T + k * PAIR + 2 * j + n] = W2[n][j * W + k];
+        for (int i = 0; i < NIN; ++i)
+            for (int j = 0; j < W; ++j) I[W1T + i * PAIR + 2 * j + n] = W1[n][j * NIN + i];
+        for (int o = 0; o < 6; ++o) {
+            for (int k = 0; k < W; ++k) I[W3R + (6 * n + o) * W3RS + k] = W3[n][o * W + k];
+            I[B3 + 6 * n + o] = b3[n][o];
+        }
+        for (int j = 0; j < W; ++j) {
+            for (int k = 0; k < NIN; ++k) I[W1P + j * W1PS + 2 * k + n] = W1[n][j * NIN + k];
+            for (int k = 0; k < W; ++k) I[W2P + j * PAIR + 2 * k + n] = W2[n][j * W + k];
+            for (int o = 0; o < 6; ++o) I[W3C + j * 12 + 2 * o + n] = W3[n][o * W + j];
+            I[B1 + 2 * j + n] = b1[n][j];
+            I[B2 + 2 * j + n] = b2[n][j];
+        }
+    }
+}
+
+static int align4(int v) { return (v + 3) & ~3; }
+
+static void build_kparams(sdempc_handle* h) {
+    KParams& k = h->kp;
+    memset(&k, 0, sizeof k);
+    const sdempc_config& c = h->cfg;
+    const sdempc_model_header& m = h->mh;
+    k.H = c.horizon; k.P = c.num_particles; k.max_iter = c.max_iter; k.max_no_improve = c.max_no_improvement_iter;
+    k.maxls = c.maxls; k.reset_option = c.reset_option; k.flags = c.flags;
+    for (int t = 0; t < SDEMPC_MAX_H; ++t) { k.dt[t] = c.dt[t]; k.sdt[t] = sqrtf(c.dt[t]); }
+    k.discount = c.discount;
+    for (int i = 0; i < SDEMPC_MAX_NU; ++i) { k.u_lo[i] = c.u_lo[i]; k.u_hi[i] = c.u_hi[i]; k.uref[i] = c.uref[i]; }
+    k.uerr = c.uerr;
+    for (int i = 0; i < 3; ++i) { k.perr[i] = c.perr[i]; k.verr[i] = c.verr[i]; k.qerr[i] = c.qerr[i]; k.werr[i] = c.werr[i]; }
+    k.res_mult = c.res_mult; k.slew = c.u_slew_coeff;
+    k.init_step = c.init_stepsize; k.max_step = c.max_stepsize; k.coef = c.coef; k.dec_f = c.decrease_factor;
+    k.inc_f = c.increase_factor; k.atol = c.atol; k.rtol = c.rtol;
+    // derived model constants: one IEEE float operation each (the oracle derives them identically)
+    k.inv_m = 1.0f / m.mass; k.grav = m.gravity; k.kT = m.k_thrust; k.kT2 = 2.0f * m.k_thrust;
+    for (int i = 0; i < 3; ++i) { k.J[i] = m.inertia[i]; k.Jinv[i] = 1.0f / m.inertia[i]; }
+    k.Jd[0] = m.inertia[2] - m.inertia[1]; k.Jd[1] = m.inertia[0] - m.inertia[2]; k.Jd[2] = m.inertia[1] - m.inertia[0];
+    for (int r = 0; r < 3; ++r)
+        for (int i = 0; i < SDEMPC_MAX_NU; ++i) k.mixer[r][i] = m.mixer[r * SDEMPC_MAX_NU + i];
+    for (int i = 0; i < 6; ++i) k.sig0[i] = m.sigma_prior[i];
+    // per-warp shared layout
+    const int H = c.horizon, NU = c.nu, W = m.width, n = align4(H * NU);
+    int o = 0;
+    k.o_xk = o; o += n; k.o_yk = o; o += n; k.o_g = o; o += n; k.o_xp = o; o += n;
+    k.o_uprev = o; o += 8;
+    k.o_xref = o; o += (H + 1) * 16;
+    k.o_xi = o; o += H * 8;
+    k.o_xtape = o; o += (H + 1) * 16;
+    k.o_stape = o; o += H * 20;
+    k.o_bufA = o; o += 2 * W; k.o_bufB = o; o += 2 * W;
+    k.o_act3 = o; o += 2 * W + 8;
+    k.o_lz = o; o += 24;
+    k.o_red = o; o += 8;
+    const bool tape_smem = (W == 32);
+    k.o_mtape = o;
+    if (tape_smem) o += H * 4 * W;
+    k.ws_stride = align4(o) + 4;   // +4 floats: skew consecutive warp regions across banks
+    k.team_stride = 16;
+    const KernelChoice& kc = h->kc;
+    const size_t floats = (size_t)kc.wsmem_floats + 4 + (size_t)kc.G * k.team_stride + (size_t)kc.G * kc.P * k.ws_stride;
+    h->smem_bytes = floats * 4;
+}
+
+static int ensure_device(sdempc_handle* h) {
+    if (h->dev_ready) return 0;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SDEMPC_ECUDA, "no usable CUDA device (%s); the MPC solve has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (h->device < 0 || h->device >= ndev) return fail(SDEMPC_EINVAL, "device %d out of range (have %d)", h->device, ndev);
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major != 10)
+        return fail(SDEMPC_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", h->device, prop.major, prop.minor);
+    h->sm_count = prop.multiProcessorCount;
+    if (h->smem_bytes > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(SDEMPC_EINVAL, "configuration needs %zu bytes of shared memory per CTA (limit %zu)", h->smem_bytes,
+                    (size_t)prop.sharedMemPerBlockOptin);
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev0));
+    CUDA_TRY(cudaEventCreate(&h->ev1));
+    CUDA_TRY(cudaMalloc(&h->d_wimg, h->wimg.size() * 4));
+    CUDA_TRY(cudaMemcpy(h->d_wimg, h->wimg.data(), h->wimg.size() * 4, cudaMemcpyHostToDevice));
+    if (!h->traj_int.empty()) {
+        CUDA_TRY(cudaMalloc(&h->d_traj, h->traj_int.size() * 4));
+        CUDA_TRY(cudaMemcpy(h->d_traj, h->traj_int.data(), h->traj_int.size() * 4, cudaMemcpyHostToDevice));
+    }
+    for (auto fn : {h->kc.solve, h->kc.rollout, h->kc.closed}) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    }
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, h->kc.solve));
+    h->regs = fa.numRegs;
+    h->dev_ready = true;
+    return 0;
+}
+
+static int grid_for(const sdempc_handle* h, int B) {
+    const int ctas = (B + h->kc.G - 1) / h->kc.G;
+    return std::max(1, std::min(ctas, h->sm_count));   // one persistent CTA per SM at most
+}
+
+static int ensure_mtape(sdempc_handle* h, int grid) {
+    if (h->mh.width == 32) return 0;
+    const size_t warps = (size_t)grid * h->kc.G * h->kc.P;
+    if (warps <= h->mtape_warps) return 0;
+    if (h->d_mtape) cudaFree(h->d_mtape);
+    h->d_mtape = nullptr;
+    CUDA_TRY(cudaMalloc(&h->d_mtape, warps * (size_t)h->cfg.horizon * 2 * h->mh.width * sizeof(float2)));
+    h->mtape_warps = warps;
+    return 0;
+}
+
+static int ensure_io(sdempc_handle* h, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > h->in_cap) {
+        if (h->d_in) cudaFree(h->d_in);
+        if (h->h_in) cudaFreeHost(h->h_in);
+        h->d_in = nullptr; h->h_in = nullptr; h->in_cap = 0;
+        const size_t cap = in_bytes + in_bytes / 4 + 4096;
+        CUDA_TRY(cudaMalloc(&h->d_in, cap));
+        CUDA_TRY(cudaMallocHost(&h->h_in, cap));
+        h->in_cap = cap;
+    }
+    if (out_bytes > h->out_cap) {
+        if (h->d_out) cudaFree(h->d_out);
+        if (h->h_out) cudaFreeHost(h->h_out);
+        h->d_out = nullptr; h->h_out = nullptr; h->out_cap = 0;
+        const size_t cap = out_bytes + out_bytes / 4 + 4096;
+        CUDA_TRY(cudaMalloc(&h->d_out, cap));
+        CUDA_TRY(cudaMallocHost(&h->h_out, cap));
+        h->out_cap = cap;
+    }
+    return 0;
+}
+
+// Sequential packer of 16-byte aligned sub-buffers into the pinned IN block.
+struct Packer {
+    char* hbase; char* dbase; size_t off = 0;
+    template <typename T>
+    const T* put(const T* src, size_t count) {
+        if (src == nullptr) return nullptr;
+        const size_t bytes = count * sizeof(T);
+        if (hbase) memcpy(hbase + off, src, bytes);
+        const T* d = reinterpret_cast<const T*>(dbase + off);
+        off += (bytes + 15) & ~(size_t)15;
+        return d;
+    }
+    template <typename T>
+    T* reserve(size_t count) {
+        T* d = reinterpret_cast<T*>(dbase + off);
+        off += (count * sizeof(T) + 15) & ~(size_t)15;
+        return d;
+    }
+};
+
+static size_t a16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+static int check_solve_args(const sdempc_handle* h, const sdempc_solve_args* a) {
+    if (!a || a->B < 1) return fail(SDEMPC_EINVAL, "B must be >= 1");
+    if (!a->x || !a->u_plan || !a->x_evol || !a->info) return fail(SDEMPC_EINVAL, "x, u_plan, x_evol and info are required");
+    if (!a->xref_win && !a->curr_t && !a->xdes) return fail(SDEMPC_EINVAL, "one of xref_win, curr_t, xdes is required");
+    if (!a->xref_win && a->curr_t && h->traj_int.empty())
+        return fail(SDEMPC_ESTATE, "trajectory mode (curr_t) needs sdempc_set_trajectory() first");
+    if (!a->rng && !a->xi_override) return fail(SDEMPC_EINVAL, "rng is required unless xi_override is given");
+    return 0;
+}
+
+// Stage inputs of a solve into pinned memory + async H2D; fills h->staged.
+static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
+    int rc = check_solve_args(h, a);
+    if (rc) return rc;
+    if ((rc = ensure_device(h))) return rc;
+    const int B = a->B, H = h->cfg.horizon, NU = h->cfg.nu, P = h->cfg.num_particles, n = H * NU;
+    const bool use_win = a->xref_win != nullptr, use_t = !use_win && a->curr_t != nullptr;
+    size_t in_bytes = a16((size_t)B * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * sizeof(sdempc_info)) + 64;
+    if (use_win) in_bytes += a16((size_t)B * (H + 1) * NX * 4);
+    else if (use_t) in_bytes += a16((size_t)B * 4);
+    else in_bytes += a16((size_t)B * NX * 4);
+    if (a->xi_override) in_bytes += a16((size_t)B * P * H * 6 * 4);
+    else in_bytes += a16((size_t)B * 16);
+    const size_t out_bytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * sizeof(sdempc_info)) + 64;
+    if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
+    const int grid = grid_for(h, B);
+    if ((rc = ensure_mtape(h, grid))) return rc;
+    if (a->trace) {
+        const size_t tb = (size_t)B * h->cfg.max_iter * SDEMPC_TRACE_W * 4;
+        if (tb > h->trace_cap) {
+            if (h->d_trace) cudaFree(h->d_trace);
+            h->d_trace = nullptr;
+            CUDA_TRY(cudaMalloc(&h->d_trace, tb));
+            h->trace_cap = tb;
+        }
+        CUDA_TRY(cudaMemsetAsync(h->d_trace, 0, tb, h->stream));
+    }
+    KParams k = h->kp;
+    Packer pk{h->h_in, h->d_in};
+    k.B = B;
+    k.x = pk.put(a->x, (size_t)B * NX);
+    k.u_plan = const_cast<float*>(pk.put(a->u_plan, (size_t)B * n));
+    k.info = const_cast<sdempc_info*>(pk.put(a->info, (size_t)B));
+    k.xref_win = use_win ? pk.put(a->xref_win, (size_t)B * (H + 1) * NX) : nullptr;
+    k.curr_t = use_t ? pk.put(a->curr_t, (size_t)B) : nullptr;
+    k.xdes = (!use_win && !use_t) ? pk.put(a->xdes, (size_t)B * NX) : nullptr;
+    k.xi_override = a->xi_override ? pk.put(a->xi_override, (size_t)B * P * H * 6) : nullptr;
+    k.rng = a->xi_override ? nullptr : reinterpret_cast<const unsigned long long*>(pk.put(a->rng, (size_t)B * 2));
+    CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, pk.off, cudaMemcpyHostToDevice, h->stream));
+    Packer po{nullptr, h->d_out};
+    k.x_evol = po.reserve<float>((size_t)B * (H + 1) * NX);
+    k.u_plan_out = po.reserve<float>((size_t)B * n);
+    k.info_out = po.reserve<sdempc_info>((size_t)B);
+    k.trace = a->trace ? h->d_trace : nullptr;
+    k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
+    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid;
+    return 0;
+}
+
+static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
+    const int threads = h->kc.G * h->kc.P * 32;
+    void* args[] = {const_cast<KParams*>(&k)};
+    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, h->smem_bytes, h->stream));
+    h->launches += 1;
+    return 0;
+}
+
+static int fetch_solve(sdempc_handle* h, const sdempc_solve_args* a) {
+    if (!h->staged_ok || a->B != h->staged_B) return fail(SDEMPC_ESTATE, "fetch without a matching stage");
+    const int B = a->B, H = h->cfg.horizon, NU = h->cfg.nu, n = H * NU;
+    const size_t o_x = 0, o_p = a16((size_t)B * (H + 1) * NX * 4), o_i = o_p + a16((size_t)B * n * 4);
+    const size_t total = o_i + a16((size_t)B * sizeof(sdempc_info));
+    CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    memcpy(a->x_evol, h->h_out + o_x, (size_t)B * (H + 1) * NX * 4);
+    memcpy(a->u_plan, h->h_out + o_p, (size_t)B * n * 4);
+    memcpy(a->info, h->h_out + o_i, (size_t)B * sizeof(sdempc_info));
+    for (int b = 0; b < B; ++b) a->info[b].solve_time_us = h->last_ms * 1000.f;
+    if (a->trace) {
+        CUDA_TRY(cudaMemcpy(a->trace, h->d_trace, (size_t)B * h->cfg.max_iter * SDEMPC_TRACE_W * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* sdempc_last_error(void) { return g_err.c_str(); }
+const char* sdempc_version(void) { return "sdempc 0.1 (sm_100a, SPEC-ARITH 1)"; }
+
+int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbytes, int device, sdempc_t** out) {
+    if (!cfg || !model_blob || !out) return fail(SDEMPC_EINVAL, "null argument");
+    if (nbytes < sizeof(sdempc_model_header)) return fail(SDEMPC_EINVAL, "model blob too small");
+    sdempc_model_header mh;
+    memcpy(&mh, model_blob, sizeof mh);
+    if (mh.magic != SDEMPC_MODEL_MAGIC || mh.version != SDEMPC_MODEL_VERSION) return fail(SDEMPC_EINVAL, "bad model magic/version");
+    if (mh.n_hidden != 2 || mh.n_out != 6 || mh.n_in != 6 + mh.nu) return fail(SDEMPC_EINVAL, "unsupported network shape");
+    if (cfg->nu != mh.nu) return fail(SDEMPC_EINVAL, "config nu=%d does not match model nu=%d", cfg->nu, mh.nu);
+    if (cfg->horizon < 1 || cfg->horizon > SDEMPC_MAX_H) return fail(SDEMPC_EINVAL, "horizon out of range 1..%d", SDEMPC_MAX_H);
+    if (cfg->max_iter < 1 || cfg->maxls < 0) return fail(SDEMPC_EINVAL, "max_iter must be >= 1 and maxls >= 0");
+    const int W = mh.width, NIN = mh.n_in;
+    const size_t per_net = (size_t)W * NIN + W + (size_t)W * W + W + 6 * (size_t)W + 6;
+    if (nbytes < sizeof mh + 2 * per_net * 4) return fail(SDEMPC_EINVAL, "model blob truncated");
+    const KernelChoice* kc = nullptr;
+    for (const auto& c : choices())
+        if (c.nu == mh.nu && c.W == W && c.P == cfg->num_particles) kc = &c;
+    if (!kc)
+        return fail(SDEMPC_EINVAL, "no compiled kernel for nu=%d width=%d particles=%d (see choices() in sdempc_api.cu)", mh.nu, W,
+                    cfg->num_particles);
+    sdempc_handle* h = new sdempc_handle();
+    h->cfg = *cfg; h->mh = mh; h->device = device; h->kc = *kc;
+    h->weights.resize(2 * per_net);
+    memcpy(h->weights.data(), (const char*)model_blob + sizeof mh, 2 * per_net * 4);
+    pack_weights(h);
+    build_kparams(h);
+    *out = h;
+    return 0;
+}
+
+void sdempc_destroy(sdempc_t* h) {
+    if (!h) return;
+    if (h->dev_ready) {
+        cudaSetDevice(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        cudaFree(h->d_wimg); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_in); cudaFree(h->d_out);
+        cudaFree(h->d_trace); cudaFree(h->d_flush);
+        if (h->h_in) cudaFreeHost(h->h_in);
+        if (h->h_out) cudaFreeHost(h->h_out);
+        if (h->ev0) cudaEventDestroy(h->ev0);
+        if (h->ev1) cudaEventDestroy(h->ev1);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+int sdempc_set_trajectory(sdempc_t* h, const float* table, int T) {
+    if (!h || !table || T < 2) return fail(SDEMPC_EINVAL, "trajectory needs at least 2 rows");
+    std::vector<float> ext(table, table + (size_t)T * 14), in((size_t)T * 14);
+    const bool enu = (h->cfg.flags & SDEMPC_F_FRAME_ENU) != 0;
+    for (int r = 0; r < T; ++r) {
+        const float* a = table + (size_t)r * 14;
+        float* b = in.data() + (size_t)r * 14;
+        if (r > 0 && !(a[0] > a[-14])) return fail(SDEMPC_EINVAL, "trajectory times must be strictly increasing (row %d)", r);
+        b[0] = a[0];
+        if (enu) {
+            const float s = 0.70710678118654752440f;
+            float c0 = s * (a[7] + a[10]), c1 = s * (a[8] + a[9]), c2 = s * (a[8] - a[9]), c3 = s * (a[7] - a[10]);
+            if (c0 < 0) { c0 = -c0; c1 = -c1; c2 = -c2; c3 = -c3; }
+            b[1] = a[2]; b[2] = a[1]; b[3] = -a[3];
+            b[4] = a[5]; b[5] = a[4]; b[6] = -a[6];
+            b[7] = c0; b[8] = c1; b[9] = c2; b[10] = c3;
+            b[11] = a[11]; b[12] = -a[12]; b[13] = -a[13];
+        } else {
+            for (int i = 1; i < 14; ++i) b[i] = a[i];
+        }
+        if (r > 0) {
+            float d = 0;
+            for (int i = 7; i < 11; ++i) d += b[i] * b[i - 14];
+            if (d < 0) for (int i = 7; i < 11; ++i) b[i] = -b[i];
+        }
+    }
+    h->traj_ext.swap(ext); h->traj_int.swap(in); h->T = T;
+    if (h->dev_ready) {
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        if (h->d_traj) cudaFree(h->d_traj);
+        h->d_traj = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_traj, h->traj_int.size() * 4));
+        CUDA_TRY(cudaMemcpy(h->d_traj, h->traj_int.data(), h->traj_int.size() * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int sdempc_state_from_traj(const sdempc_t* h, const float* t, int n, float* out) {
+    if (!h || !t || !out) return fail(SDEMPC_EINVAL, "null argument");
+    if (h->traj_ext.empty()) return fail(SDEMPC_ESTATE, "no trajectory set");
+    const float* tab = h->traj_ext.data();
+    const int T = h->T;
+    for (int q = 0; q < n; ++q) {
+        float* o = out + (size_t)q * NX;
+        const float tt = t[q];
+        int lo = 0, hi = T - 1;
+        if (tt <= tab[0]) { for (int i = 0; i < NX; ++i) o[i] = tab[1 + i]; }
+        else if (tt >= tab[(size_t)hi * 14]) { for (int i = 0; i < NX; ++i) o[i] = tab[(size_t)hi * 14 + 1 + i]; }
+        else {
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (tab[(size_t)mid * 14] <= tt) lo = mid; else hi = mid; }
+            const float *a = tab + (size_t)lo * 14, *b = a + 14;
+            const float al = (tt - a[0]) / (b[0] - a[0]);
+            for (int i = 0; i < NX; ++i) o[i] = fmaf(al, b[1 + i] - a[1 + i], a[1 + i]);
+        }
+        const float n2 = fmaf(o[9], o[9], fmaf(o[8], o[8], fmaf(o[7], o[7], o[6] * o[6])));
+        const float inv = 1.0f / sqrtf(n2);
+        for (int i = 6; i < 10; ++i) o[i] = o[i] * inv;
+    }
+    return 0;
+}
+
+int sdempc_reset(sdempc_t* h, int B, const float* x, const float* xdes, float* u_plan, sdempc_info* info) {
+    (void)x; (void)xdes;
+    if (!h || B < 1 || !u_plan || !info) return fail(SDEMPC_EINVAL, "bad argument");
+    const sdempc_config& c = h->cfg;
+    for (int b = 0; b < B; ++b) {
+        for (int t = 0; t < c.horizon; ++t)
+            for (int i = 0; i < c.nu; ++i) {
+                float v = c.uref[i];
+                v = v < c.u_lo[i] ? c.u_lo[i] : v;
+                v = v > c.u_hi[i] ? c.u_hi[i] : v;
+                u_plan[((size_t)b * c.horizon + t) * c.nu + i] = v;
+            }
+        memset(&info[b], 0, sizeof(sdempc_info));
+        info[b].stepsize = c.init_stepsize;
+    }
+    return 0;
+}
+
+int sdempc_stage(sdempc_t* h, const sdempc_solve_args* args) {
+    if (!h) return fail(SDEMPC_EINVAL, "null handle");
+    return stage_solve(h, args);
+}
+
+int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
+    if (!h || !h->staged_ok) return fail(SDEMPC_ESTATE, "sdempc_stage() first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t FL = (size_t)256 << 20;
+    if (flush_l2 && !h->d_flush) CUDA_TRY(cudaMalloc(&h->d_flush, FL));
+    for (int i = 0; i < n; ++i) {
+        if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+        int rc = launch(h, h->kc.solve, h->staged, h->last_grid);
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(cudaEventSynchronize(h->ev1));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+        h->last_ms = t;
+        if (ms) ms[i] = t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args) {
+    if (!h || !args) return fail(SDEMPC_EINVAL, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return fetch_solve(h, args);
+}
+
+int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
+    if (!h) return fail(SDEMPC_EINVAL, "null handle");
+    int rc = stage_solve(h, a);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = launch(h, h->kc.solve, h->staged, h->last_grid))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, h->ev0, h->ev1));
+    h->last_ms = t;
+    for (int b = 0; b < a->B; ++b) a->info[b].solve_time_us = t * 1000.f;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sdempc_solve(sdempc_t* h, int B, const float* x, const float* curr_t, const float* xdes, const uint64_t* rng, float* u_plan,
+                 float* x_evol, sdempc_info* info, const float* xi_override) {
+    sdempc_solve_args a;
+    memset(&a, 0, sizeof a);
+    a.B = B; a.x = x; a.curr_t = curr_t; a.xdes = xdes; a.rng = rng; a.u_plan = u_plan; a.x_evol = x_evol; a.info = info;
+    a.xi_override = xi_override;
+    return sdempc_solve_ex(h, &a);
+}
+
+int sdempc_rollout(sdempc_t* h, int B, const float* x, const float* curr_t, const float* xdes, const float* xref_win,
+                   const uint64_t* rng, const float* xi_override, const float* u, const float* u_prev, float* cost, float* grad,
+                   float* x_evol) {
+    if (!h || B < 1 || !x || !u || !u_prev || !cost) return fail(SDEMPC_EINVAL, "bad argument");
+    if (!xref_win && !curr_t && !xdes) return fail(SDEMPC_EINVAL, "one of xref_win, curr_t, xdes is required");
+    if (!xref_win && curr_t && h->traj_int.empty()) return fail(SDEMPC_ESTATE, "trajectory mode needs sdempc_set_trajectory() first");
+    if (!rng && !xi_override) return fail(SDEMPC_EINVAL, "rng is required unless xi_override is given");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    const int H = h->cfg.horizon, NU = h->cfg.nu, P = h->cfg.num_particles, n = H * NU;
+    const bool use_win = xref_win != nullptr, use_t = !use_win && curr_t != nullptr;
+    size_t in_bytes = a16((size_t)B * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * NU * 4) + 64 +
+                      a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * P * H * 6 * 4 + (size_t)B * 16);
+    const size_t out_bytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * 4) + 64;
+    if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
+    const int grid = grid_for(h, B);
+    if ((rc = ensure_mtape(h, grid))) return rc;
+    KParams k = h->kp;
+    Packer pk{h->h_in, h->d_in};
+    k.B = B;
+    k.x = pk.put(x, (size_t)B * NX);
+    k.u_in = pk.put(u, (size_t)B * n);
+    k.uprev_in = pk.put(u_prev, (size_t)B * NU);
+    k.xref_win = use_win ? pk.put(xref_win, (size_t)B * (H + 1) * NX) : nullptr;
+    k.curr_t = use_t ? pk.put(curr_t, (size_t)B) : nullptr;
+    k.xdes = (!use_win && !use_t) ? pk.put(xdes, (size_t)B * NX) : nullptr;
+    k.xi_override = xi_override ? pk.put(xi_override, (size_t)B * P * H * 6) : nullptr;
+    k.rng = xi_override ? nullptr : reinterpret_cast<const unsigned long long*>(pk.put(rng, (size_t)B * 2));
+    CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, pk.off, cudaMemcpyHostToDevice, h->stream));
+    Packer po{nullptr, h->d_out};
+    k.x_evol = po.reserve<float>((size_t)B * (H + 1) * NX);
+    float* d_grad = po.reserve<float>((size_t)B * n);
+    k.grad_out = grad ? d_grad : nullptr;
+    k.cost_out = po.reserve<float>((size_t)B);
+    k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
+    h->staged_ok = false;
+    if ((rc = launch(h, h->kc.rollout, k, grid))) return rc;
+    h->last_grid = grid;
+    CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, po.off, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    const size_t o_p = a16((size_t)B * (H + 1) * NX * 4), o_c = o_p + a16((size_t)B * n * 4);
+    if (x_evol) memcpy(x_evol, h->h_out, (size_t)B * (H + 1) * NX * 4);
+    if (grad) memcpy(grad, h->h_out + o_p, (size_t)B * n * 4);
+    memcpy(cost, h->h_out + o_c, (size_t)B * 4);
+    return 0;
+}
+
+int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const float* t0, const uint64_t* rng, float* x_hist,
+                       float* u_hist, float* stats) {
+    if (!h || R < 1 || ticks < 1 || !x0 || !t0 || !rng || !stats) return fail(SDEMPC_EINVAL, "bad argument");
+    if (h->traj_int.empty()) return fail(SDEMPC_ESTATE, "closed loop needs sdempc_set_trajectory() first");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    const int NU = h->cfg.nu;
+    const size_t in_bytes = a16((size_t)R * NX * 4) + a16((size_t)R * 4) + a16((size_t)R * 16) + 64;
+    const size_t xh = x_hist ? a16((size_t)R * (ticks + 1) * NX * 4) : 0, uh = u_hist ? a16((size_t)R * ticks * NU * 4) : 0;
+    const size_t out_bytes = a16((size_t)R * 16) + xh + uh + 64;
+    if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
+    const int grid = grid_for(h, R);
+    if ((rc = ensure_mtape(h, grid))) return rc;
+    KParams k = h->kp;
+    Packer pk{h->h_in, h->d_in};
+    k.B = R; k.ticks = ticks;
+    k.x = pk.put(x0, (size_t)R * NX);
+    k.t0 = pk.put(t0, (size_t)R);
+    k.rng = reinterpret_cast<const unsigned long long*>(pk.put(rng, (size_t)R * 2));
+    CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, pk.off, cudaMemcpyHostToDevice, h->stream));
+    Packer po{nullptr, h->d_out};
+    k.stats = po.reserve<float>((size_t)R * 4);
+    k.x_hist = x_hist ? po.reserve<float>((size_t)R * (ticks + 1) * NX) : nullptr;
+    k.u_hist = u_hist ? po.reserve<float>((size_t)R * ticks * NU) : nullptr;
+    k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
+    h->staged_ok = false;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = launch(h, h->kc.closed, k, grid))) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    h->last_grid = grid;
+    CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, po.off, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    size_t off = 0;
+    memcpy(stats, h->h_out + off, (size_t)R * 16); off += a16((size_t)R * 16);
+    if (x_hist) { memcpy(x_hist, h->h_out + off, (size_t)R * (ticks + 1) * NX * 4); off += xh; }
+    if (u_hist) { memcpy(u_hist, h->h_out + off, (size_t)R * ticks * NU * 4); off += uh; }
+    return 0;
+}
+
+int64_t sdempc_launch_count(const sdempc_t* h) { return h ? h->launches : 0; }
+
+int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
+    if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
+    out[0] = h->kc.G * h->kc.P * 32;
+    out[1] = (int32_t)h->smem_bytes;
+    out[2] = h->kc.G;
+    out[3] = h->regs;
+    out[4] = h->last_grid;
+    out[5] = h->sm_count;
+    return 0;
+}
+
+}  // extern "C"
