@@ -458,7 +458,7 @@ static REAL FN(rollout)(const sdempc_config* c, const OMODEL* m, const REAL* x0,
             OSTEP* st = &steps[t];
             st->disc = disc;
             const REAL* up = (t == 0) ? uprev0 : u + (size_t)(t - 1) * nu;
-            const REAL dt = (REAL)c->dt[t], sdt = (REAL)sqrtf(c->dt[t]);
+            const REAL dt = (REAL)c->dt[t], sdt = R_SQRT((REAL)c->dt[t]);
             const REAL l = FN(step_fwd)(c, m, st, u + (size_t)t * nu, up, xref + (size_t)(t + 1) * NX,
                                         xi + ((size_t)p * H + t) * 6, dt, sdt);
             Jp = FMA(disc, l, Jp);
@@ -480,7 +480,7 @@ static REAL FN(rollout)(const sdempc_config* c, const OMODEL* m, const REAL* x0,
             for (int i = 0; i < nu; ++i) gp[i] = 0;
             for (int t = H - 1; t >= 0; --t) {
                 const REAL* up = (t == 0) ? uprev0 : u + (size_t)(t - 1) * nu;
-                const REAL dt = (REAL)c->dt[t], sdt = (REAL)sqrtf(c->dt[t]);
+                const REAL dt = (REAL)c->dt[t], sdt = R_SQRT((REAL)c->dt[t]);
                 FN(step_bwd)(c, m, &steps[t], u + (size_t)t * nu, up, xref + (size_t)(t + 1) * NX,
                              xi + ((size_t)p * H + t) * 6, dt, sdt, lam, gu, gn);
                 for (int i = 0; i < nu; ++i) { gpart[t * nu + i] = gu[i] + gp[i]; gp[i] = gn[i]; }
@@ -818,7 +818,7 @@ int FN(closed_loop)(void* hv, int Rn, int ticks, const REAL* x0s, const REAL* t0
         REAL se = 0, me = 0, sc = 0, sn = 0;
         const uint64_t seed = rng[2 * (size_t)r];
         uint64_t tick = rng[2 * (size_t)r + 1];
-        const REAL dt0 = (REAL)c->dt[0], sdt0 = (REAL)sqrtf(c->dt[0]);
+        const REAL dt0 = (REAL)c->dt[0], sdt0 = R_SQRT((REAL)c->dt[0]);
         for (int k = 0; k < ticks; ++k, ++tick) {
             if (x_hist) { FN(to_ext)(h, x, xe, 1); for (int i = 0; i < NX; ++i) x_hist[((size_t)r * (ticks + 1) + k) * NX + i] = xe[i]; }
             REAL tw = FMA((REAL)k, dt0, t0s[r]);

@@ -1,0 +1,56 @@
+"""Static sharding of independent MPC problems across ranks.
+
+One process per GPU; problem index range [0, B) is split into contiguous blocks, each
+rank solves its block with no collective on the data path, and the only exchange is the
+final result gather (plan + predicted trajectory + telemetry, about 1.5 KB per problem).
+``torch.distributed`` is plumbing only (NCCL on GPU boxes, gloo in CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(B: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of rank ``rank``: sizes differ by at most one, earlier ranks get the extra."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_problem(problem: dict, rank: int, world: int) -> dict:
+    B = next(iter(problem.values())).shape[0]
+    lo, hi = shard_range(B, rank, world)
+    return {k: v[lo:hi] for k, v in problem.items()}
+
+
+def gather_results(local: dict, B: int, device=None) -> dict | None:
+    """All ranks call this; rank 0 receives the concatenated [B, ...] float32 arrays, the others None.
+    Uses one all_gather of a padded flat float32 buffer (NCCL has no gatherv)."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    keys = sorted(local.keys())
+    flat = np.concatenate([np.ascontiguousarray(local[k], np.float32).reshape(local[k].shape[0], -1) for k in keys], axis=1)
+    widths = [int(np.prod(local[k].shape[1:])) for k in keys]
+    shapes = [local[k].shape[1:] for k in keys]
+    max_rows = max(shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world))
+    pad = np.zeros((max_rows, flat.shape[1]), np.float32)
+    pad[: flat.shape[0]] = flat
+    t = torch.from_numpy(pad)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    if rank != 0:
+        return None
+    rows = []
+    for r in range(world):
+        lo, hi = shard_range(B, r, world)
+        rows.append(out[r][: hi - lo].cpu().numpy())
+    allf = np.concatenate(rows, axis=0)
+    res, off = {}, 0
+    for k, w, s in zip(keys, widths, shapes):
+        res[k] = allf[:, off: off + w].reshape((B,) + tuple(s))
+        off += w
+    return res

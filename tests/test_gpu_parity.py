@@ -1,0 +1,275 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  SPEC-ARITH makes the two bit-identical, so every comparison is exact equality — stronger than
+the 1e-4 relative bar of BASELINE.json's north_star; `test_tolerance_statement` spells the bar out."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_setup, random_states
+from sde4mbrl_px4_b200 import synthetic, trajectory
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from sde4mbrl_px4_b200 import solver as s
+
+    return s
+
+
+def _pair(solver, O, vehicle, mode, enu=True, **ov):
+    cfg, blob, model = make_setup(vehicle, mode, enu=enu, **ov)
+    return cfg, solver.MPCSolver(cfg, blob), O.Oracle(cfg, blob, "f32")
+
+
+def _eq(a, b, what):
+    assert np.array_equal(a, b), f"{what}: max abs diff {np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max():.3e}"
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+
+
+def test_cuda_reproduces_golden_vectors():
+    from golden import make_golden
+
+    z = np.load(GOLDEN)
+    meta = json.loads(str(z["meta"]))
+    for case in meta["cases"]:
+        out = make_golden.run_case(case, backend="cuda")
+        for k, v in out.items():
+            _eq(v, z[f"{case['name']}/{k}"], f"{case['name']}/{k}")
+
+
+@pytest.mark.parametrize("vehicle,P,width", [("iris", 1, None), ("iris", 2, None), ("iris", 4, None), ("iris", 8, None),
+                                             ("hexa", 1, None), ("hexa", 8, None), ("hexa", 1, 32), ("hexa", 8, 32),
+                                             ("iris", 1, 64)])
+@pytest.mark.parametrize("enu", [True, False])
+def test_rollout_value_and_grad(solver, O, vehicle, P, width, enu):
+    """Kernels A+B: particle rollout, cost and adjoint, every compiled (nu, width, particles) combination."""
+    ov = dict(num_particles=P)
+    if width:
+        ov["width"] = width
+    cfg, s, o = _pair(solver, O, vehicle, "traj", enu=enu, **ov)
+    B = 13   # ragged: not a multiple of the problems-per-CTA of any kernel
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=P)
+    rng = np.random.default_rng(7)
+    u = np.clip(np.array(cfg.uref[: cfg.nu]) + 0.08 * rng.standard_normal((B, cfg.horizon, cfg.nu)), 1e-4, 1).astype(np.float32)
+    up = np.clip(np.array(cfg.uref[: cfg.nu]) + 0.05 * rng.standard_normal((B, cfg.nu)), 1e-4, 1).astype(np.float32)
+    J, g, xe = s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"])
+    Jo, go, xeo = o.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"])
+    _eq(J, Jo, "cost"); _eq(g, go, "grad"); _eq(xe, xeo, "x_evol")
+    # explicit noise tensor (test hook) and forward-only call
+    xi = rng.standard_normal((B, P, cfg.horizon, 6)).astype(np.float32)
+    J2, g2, _ = s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], xi=xi, want_grad=False)
+    Jo2, _, _ = o.rollout(pr["x"], u, up, xref_win=pr["xref_win"], xi=xi, want_grad=False)
+    _eq(J2, Jo2, "cost (xi override)")
+    assert g2 is None
+
+
+def test_reference_modes_trajectory_table_and_setpoint(solver, O):
+    cfg, s, o = _pair(solver, O, "iris", "traj")
+    tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.7, duration=12.0))
+    s.set_trajectory(tab); o.set_trajectory(tab)
+    t = np.array([-1, 0, 0.013, 3.3, 11.99, 12, 40], np.float32)
+    _eq(s.state_from_traj(t), o.state_from_traj(t), "state_from_traj")
+    B = 9
+    x = random_states(B, 3)
+    ct = np.array([0.0, 0.37, 1.0, 2.5, 5.01, 11.3, 11.9, 12.0, 30.0], np.float32)   # incl. windows clamped at the end
+    rng = np.array([[40 + b, 3] for b in range(B)], np.uint64)
+    u0, i0 = s.reset(B)
+    _eq(u0, o.reset(B)[0], "reset plan")
+    for a, b, w in zip(s.rollout(x, u0, u0[:, 0], curr_t=ct, rng=rng), o.rollout(x, u0, u0[:, 0], curr_t=ct, rng=rng), "Jgx"):
+        _eq(a, b, f"trajectory mode {w}")
+    cfgp, sp, op = _pair(solver, O, "iris", "pos")
+    xd = random_states(B, 4)
+    for a, b, w in zip(sp.rollout(x, u0, u0[:, 0], xdes=xd, rng=rng), op.rollout(x, u0, u0[:, 0], xdes=xd, rng=rng), "Jgx"):
+        _eq(a, b, f"set-point mode {w}")
+
+
+@pytest.mark.parametrize("vehicle,mode,P,iters", [("iris", "traj", 1, 200), ("iris", "pos", 1, 100), ("iris", "traj", 8, 40),
+                                                  ("hexa", "traj", 1, 60), ("hexa", "traj", 8, 25)])
+def test_free_running_solve(solver, O, vehicle, mode, P, iters):
+    """Kernel C: the whole APG loop on device, free running at the reference's iteration budget, fixed
+    iteration count (rtol = atol = 0): plan, predicted trajectory, telemetry and the per-iteration decision
+    trace (f_y, J trial, step, n_ls, accept, J_x, |g|^2, k) are all identical to the oracle."""
+    cfg, s, o = _pair(solver, O, vehicle, mode, num_particles=P, max_iter=iters, rtol=0.0, atol=0.0)
+    B = 24 if P == 1 else 5
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=11 + P)
+    kw = dict(xref_win=pr["xref_win"]) if mode == "traj" else dict(xdes=pr["xref_win"][:, 5])
+    u0, i0 = s.reset(B)
+    u, xe, info, tr = s.solve(pr["x"], u0, i0, rng=pr["rng"], want_trace=True, **kw)
+    uo, xeo, infoo, tro = o.solve(pr["x"], u0, i0, rng=pr["rng"], want_trace=True, **kw)
+    _eq(tr, tro, "decision trace"); _eq(u, uo, "u*"); _eq(xe, xeo, "x_evol"); _eq(info[:, :7], infoo[:, :7], "telemetry")
+    assert np.all(info[:, 2] == iters) and np.all(info[:, 7] > 0)
+    # second tick: warm start (shift + carried step size), new noise tick
+    rng2 = pr["rng"].copy(); rng2[:, 1] += 1
+    u2, xe2, info2, _ = s.solve(xe[:, 1], u, info, rng=rng2, **kw)
+    uo2, xeo2, infoo2, _ = o.solve(xeo[:, 1], uo, infoo, rng=rng2, **kw)
+    _eq(u2, uo2, "tick 2 u*"); _eq(xe2, xeo2, "tick 2 x_evol"); _eq(info2[:, :7], infoo2[:, :7], "tick 2 telemetry")
+
+
+def test_early_stopping_with_yaml_tolerances(solver, O):
+    """Default YAML tolerances (rtol 1e-6, atol 1e-8): per-problem iteration counts differ and still match."""
+    cfg, s, o = _pair(solver, O, "iris", "pos")
+    B = 16
+    x = random_states(B, 8)
+    xd = x.copy(); xd[:, 0:3] += 0.05; xd[:, 3:6] = 0; xd[:, 10:13] = 0
+    rng = np.array([[7, b] for b in range(B)], np.uint64)
+    u0, i0 = s.reset(B)
+    a, b = s.solve(x, u0, i0, xdes=xd, rng=rng), o.solve(x, u0, i0, xdes=xd, rng=rng)
+    _eq(a[0], b[0], "u*"); _eq(a[2][:, :7], b[2][:, :7], "telemetry")
+
+
+def test_tolerance_statement(solver, O):
+    """north_star's bar, stated explicitly: u* and the predicted mean trajectory within 1e-4 relative (FP32)."""
+    cfg, s, o = _pair(solver, O, "iris", "traj", rtol=0.0, atol=0.0)
+    pr = synthetic.batched_problems(8, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=99)
+    u0, i0 = s.reset(8)
+    u, xe, _, _ = s.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+    uo, xeo, _, _ = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+    TOL = 1e-4
+    assert np.abs(u - uo).max() <= TOL * np.abs(uo).max()
+    assert np.abs(xe - xeo).max() <= TOL * np.abs(xeo).max()
+
+
+def test_full_size_batch_4096(solver, O):
+    """BASELINE config 4 at full size: 4096 independent iris problems, 200 iterations, bit-exact against the
+    oracle (the oracle finishes this in seconds on the host cores), plus size-independent properties."""
+    cfg, s, o = _pair(solver, O, "iris", "traj", rtol=0.0, atol=0.0)
+    B = 4096
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=0)
+    u0, i0 = s.reset(B)
+    u, xe, info, _ = s.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+    uo, xeo, infoo, _ = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+    _eq(u, uo, "u*"); _eq(xe, xeo, "x_evol"); _eq(info[:, :7], infoo[:, :7], "telemetry")
+    # properties: box respected, cost decreased, finite; result independent of batch composition
+    assert np.all(u >= np.float32(1e-4)) and np.all(u <= 1.0) and np.all(np.isfinite(xe))
+    assert np.all(info[:, 6] <= info[:, 5])
+    idx = np.array([0, 5, 1234, 4095, 77, 2048, 3000])
+    us, xs, infos, _ = s.solve(pr["x"][idx], u0[idx], i0[idx], xref_win=pr["xref_win"][idx], rng=pr["rng"][idx])
+    _eq(us, u[idx], "batch-composition invariance"); _eq(xs, xe[idx], "batch-composition invariance (x_evol)")
+    # opt_cost is the rollout cost of the returned plan
+    J, _, _ = s.rollout(pr["x"][idx], u[idx], u0[idx, 0], xref_win=pr["xref_win"][idx], rng=pr["rng"][idx], want_grad=False)
+    _eq(J, info[idx, 6], "opt_cost = J(u*)")
+    # staged launches are idempotent (the bench re-launches on staged inputs)
+    s.stage(pr["x"][:64], u0[:64], i0[:64], xref_win=pr["xref_win"][:64], rng=pr["rng"][:64])
+    ms = s.launch_timed(2, flush_l2=True)
+    a = s.fetch()
+    _eq(a[0], u[:64], "staged relaunch"); assert np.all(ms > 0)
+
+
+def test_closed_loop_monte_carlo(solver, O):
+    """BASELINE config 5 in miniature: plant + MPC ticks entirely on device, identical to the oracle's loop."""
+    cfg, s, o = _pair(solver, O, "iris", "traj", max_iter=15, rtol=0.0, atol=0.0)
+    tab = trajectory.csv_rows_to_table(trajectory.lemniscate(1.5, 10.0, 0.2, duration=20.0))
+    s.set_trajectory(tab); o.set_trajectory(tab)
+    R, ticks = 11, 12
+    x0 = synthetic.initial_states(tab[0, 1:4], R, seed=5)
+    t0 = np.linspace(0, 3, R).astype(np.float32)
+    rng = np.array([[500 + r, 0] for r in range(R)], np.uint64)
+    xh, uh, st = s.closed_loop(x0, t0, rng, ticks)
+    xho, uho, sto = o.closed_loop(x0, t0, rng, ticks)
+    _eq(uh, uho, "applied controls"); _eq(xh, xho, "plant trajectory"); _eq(st, sto, "stats")
+    # P = 8 variant
+    cfg8, s8, o8 = _pair(solver, O, "iris", "traj", max_iter=6, num_particles=8, rtol=0.0, atol=0.0)
+    s8.set_trajectory(tab); o8.set_trajectory(tab)
+    a, b = s8.closed_loop(x0[:3], t0[:3], rng[:3], 5), o8.closed_loop(x0[:3], t0[:3], rng[:3], 5)
+    _eq(a[0], b[0], "P=8 plant trajectory"); _eq(a[2], b[2], "P=8 stats")
+
+
+def test_non_finite_state_is_reported_not_fatal(solver):
+    cfg, blob, _ = make_setup("iris", "pos", max_iter=5)
+    s = solver.MPCSolver(cfg, blob)
+    x = random_states(3, 1)
+    x[1, 0] = np.nan
+    u0, i0 = s.reset(3)
+    u, xe, info, _ = s.solve(x, u0, i0, xdes=random_states(3, 2), rng=np.zeros((3, 2), np.uint64))
+    assert np.isinf(info[1, 6]) and np.isfinite(info[[0, 2], 6]).all()
+    assert np.all(np.isfinite(u[[0, 2]]))
+
+
+def test_controller_interface_end_to_end(O):
+    """load_mpc_from_cfgfile -> m_reset -> m_mpc over three ticks (the calls of sde_control.py:685-719,
+    :400-416) against the same sequence on the oracle; both controllers alive in one process."""
+    from sde4mbrl_px4_b200 import sde_mpc_design as design
+
+    cfg_dict, (m_reset, m_mpc), sft, ctl = design.load_mpc_from_cfgfile(os.path.join(ROOT, "configs", "iris_traj.yaml"), max_iter=25)
+    _, (p_reset, p_mpc), sft_pos, pctl = design.load_mpc_from_cfgfile(os.path.join(ROOT, "configs", "iris_pos.yaml"), max_iter=25)
+    assert sft is not None and sft_pos is None and abs(cfg_dict["_time_steps"][0] * 1e6 - 5e4) < 1e-2
+    o = O.Oracle(ctl.cfg, ctl.model.to_blob(), "f32"); o.set_trajectory(ctl.table)
+    op = O.Oracle(pctl.cfg, pctl.model.to_blob(), "f32")
+    x = np.array(sft(0.0)); x[0:3] += [0.2, -0.1, 0.1]
+    rng = design.PRNGKey(10)
+    st, stp = m_reset(x=x, rng=rng, xdes=x), p_reset(x=x, rng=rng, xdes=x)
+    uo, io = o.reset(1)
+    upo, ipo = op.reset(1)
+    rng_o = np.array(rng, np.uint64).reshape(1, 2)
+    for k in range(3):
+        u, st, rng, xe = m_mpc(x, rng, st, curr_t=0.05 * k, xdes=x)
+        up_, stp, _, xep = p_mpc(x, rng_o[0], stp, curr_t=0.0, xdes=np.array(sft(0.0)))   # idle-mode pattern: both per tick
+        u.block_until_ready()
+        uo, xeo, io, _ = o.solve(x[None], uo, io, curr_t=np.array([0.05 * k], np.float32), rng=rng_o)
+        upo, xepo, ipo, _ = op.solve(x[None], upo, ipo, xdes=np.array(sft(0.0))[None], rng=rng_o)
+        rng_o[:, 1] += 1
+        _eq(np.asarray(u), uo[0], f"tick {k} u"); _eq(np.asarray(xe), xeo[0], f"tick {k} x_evol")
+        _eq(np.asarray(up_), upo[0], f"tick {k} set-point u")
+        assert abs(float(st.opt_cost) - io[0, 6]) == 0 and float(st.num_steps) == 25
+        assert np.array_equal(np.asarray(rng), rng_o[0])
+        x = np.asarray(xe)[1].copy()
+
+
+def _run_script(body: str, timeout=600):
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, "-c", textwrap.dedent(body)], capture_output=True, text=True, timeout=timeout, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def test_fork_safety_and_node_harness():
+    """The node builds its solvers in the parent and solves in a forked child (sde_control.py:66-75, 723-728):
+    construction must not create a CUDA context.  Runs in a fresh interpreter (this pytest process already has one)."""
+    out = _run_script(f"""
+        import sys, time
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np
+        from sde4mbrl_px4_b200 import node
+        n = node.SDEControlNode({os.path.join(ROOT, 'configs')!r}, 'iris_traj.yaml', 'iris_pos.yaml', seed=10, use_process=True, max_iter=20)
+        try:
+            def msg(t, x=0.0):
+                return dict(time_usec=t, x=x, y=0.1, z=1.4, vx=0, vy=0, vz=0, qw=1, qx=0, qy=0, qz=0, wx=0, wy=0, wz=0)
+            assert n.mpc_state_callback(msg(1_000_000)) is None
+            assert n.wait_solve(120), "solver process did not answer (CUDA after fork?)"
+            assert n.initialize_mpc() and n.start_trajectory(node.CTRL_TEST, target_pose=(0.3, 0.1, 1.5, 1, 0, 0, 0))
+            n.mpc_state_callback(msg(1_050_000)); assert n.wait_solve(60)
+            cmd = n.mpc_state_callback(msg(1_100_000)); assert n.wait_solve(60)
+            assert cmd is not None and cmd['mpc_on'] == node.CONTROL_STATES['test']
+            assert cmd['motor_val_des'].shape == (6,) and np.all(cmd['motor_val_des'][:4] > 0) and np.all(cmd['motor_val_des'][4:] == 0)
+            rep = n.opt_state_report()
+            assert rep['num_steps'] == 20 and rep['opt_cost'] <= rep['cost_init'] and rep['solve_time'] > 0
+            # idle: both solvers within one tick
+            assert n.start_trajectory(node.CTRL_TRAJ_IDLE)
+            for k in range(4):
+                cmd = n.mpc_state_callback(msg(1_150_000 + 50_000 * k)); assert n.wait_solve(60)
+            assert n._control_state == node.CONTROL_STATES['idle']
+            assert n.start_trajectory(node.CTRL_TRAJ_ACTIVE)
+            for k in range(3):
+                cmd = n.mpc_state_callback(msg(1_400_000 + 50_000 * k)); assert n.wait_solve(60)
+            assert n._control_state == node.CONTROL_STATES['traj'] and cmd['mpc_on'] == node.CONTROL_STATES['traj']
+            print('NODE_OK', rep['solve_time'])
+        finally:
+            n.close()
+    """)
+    assert "NODE_OK" in out
