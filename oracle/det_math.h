@@ -22,7 +22,7 @@ static inline float det_rint(float t) { return (t + 12582912.0f) - 12582912.0f; 
 
 /* exp(x) for x <= 0 (clamped at -80) : Cody-Waite reduction + degree-6 Taylor, |rel err| ~ 2e-7 */
 static inline float det_exp_nonpos(float x) {
-    x = fmaxf(x, -80.0f);
+    x = x < -80.0f ? -80.0f : x;
     float n = det_rint(x * 1.44269504f);
     float r = fmaf(n, -0.693359375f, x);
     r = fmaf(n, 2.12194440e-4f, r);
@@ -46,7 +46,8 @@ static inline float det_recip12(float d) {
 }
 
 static inline float det_tanh(float x) {
-    float a = fminf(fabsf(x), 10.0f);
+    float a = fabsf(x);
+    a = a > 10.0f ? 10.0f : a;
     float e = det_exp_nonpos(-2.0f * a);
     float t = (1.0f - e) * det_recip12(1.0f + e);
     return copysignf(t, x);
@@ -80,7 +81,7 @@ static inline float det_log1p01(float e) {
 
 static inline float det_softplus(float s) {
     float e = det_exp_nonpos(-fabsf(s));
-    return fmaxf(s, 0.0f) + det_log1p01(e);
+    return (s > 0.0f ? s : 0.0f) + det_log1p01(e);
 }
 
 static inline float det_sigmoid(float s) {

@@ -20,7 +20,7 @@ __device__ __forceinline__ float det_rint(float t) { return __fadd_rn(__fadd_rn(
 
 // exp(x), x <= 0 (clamped at -80)
 __device__ __forceinline__ float det_exp_nonpos(float x) {
-    x = fmaxf(x, -80.0f);
+    x = x < -80.0f ? -80.0f : x;
     float n = det_rint(__fmul_rn(x, 1.44269504f));
     float r = fma_(n, -0.693359375f, x);
     r = fma_(n, 2.12194440e-4f, r);
@@ -44,7 +44,8 @@ __device__ __forceinline__ float det_recip12(float d) {
 }
 
 __device__ __forceinline__ float det_tanh(float x) {
-    float a = fminf(fabsf(x), 10.0f);
+    float a = fabsf(x);
+    a = a > 10.0f ? 10.0f : a;
     float e = det_exp_nonpos(__fmul_rn(-2.0f, a));
     float t = __fmul_rn(__fadd_rn(1.0f, -e), det_recip12(__fadd_rn(1.0f, e)));
     return copysignf(t, x);
@@ -52,7 +53,9 @@ __device__ __forceinline__ float det_tanh(float x) {
 
 // tanh of both halves with packed f32x2 arithmetic (same per-component sequence as det_tanh)
 __device__ __forceinline__ float2 det_tanh2(float2 x) {
-    float2 a = make_float2(fminf(fabsf(x.x), 10.0f), fminf(fabsf(x.y), 10.0f));
+    float2 a = make_float2(fabsf(x.x), fabsf(x.y));
+    a.x = a.x > 10.0f ? 10.0f : a.x;
+    a.y = a.y > 10.0f ? 10.0f : a.y;
     float2 arg = mul2_(splat(-2.0f), a);  // >= -20: the -80 clamp of det_exp_nonpos is a no-op
     float2 t = mul2_(arg, splat(1.44269504f));
     float2 n = add2_(add2_(t, splat(12582912.0f)), splat(-12582912.0f));
@@ -107,7 +110,7 @@ __device__ __forceinline__ float det_log1p01(float e) {
 // softplus(s) and sigmoid(s) share exp(-|s|)
 __device__ __forceinline__ void det_softplus_sigmoid(float s, float& sp, float& sg) {
     float e = det_exp_nonpos(-fabsf(s));
-    sp = __fadd_rn(fmaxf(s, 0.0f), det_log1p01(e));
+    sp = __fadd_rn(s > 0.0f ? s : 0.0f, det_log1p01(e));
     float r = det_recip12(__fadd_rn(1.0f, e));
     sg = s >= 0.0f ? r : __fmul_rn(e, r);
 }

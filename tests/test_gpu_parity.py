@@ -36,7 +36,7 @@ def _pair(solver, O, vehicle, mode, enu=True, **ov):
 
 
 def _eq(a, b, what):
-    assert np.array_equal(a, b), f"{what}: max abs diff {np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max():.3e}"
+    assert np.array_equal(a, b, equal_nan=True), f"{what}: max abs diff {np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max():.3e}"
 
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
