@@ -55,7 +55,9 @@ extern "C" {
 /* flags for sdempc_config.flags */
 #define SDEMPC_F_FRAME_ENU 1u      /* external frame is ENU/FLU (convert_to_enu=True, sde_control.py:685) */
 #define SDEMPC_F_NO_SHIFT 2u       /* do not shift the plan by one step at the start of a solve */
-#define SDEMPC_F_SPECULATIVE_LS 4u /* latency mode: evaluate all line-search trials concurrently */
+#define SDEMPC_F_SPECULATIVE_LS 4u /* force latency mode: all line-search trials evaluated concurrently on sibling warps */
+#define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the batched kernel (sequential line search) even for small batches;
+                                      default: latency mode when B <= number of SMs.  Results are bit-identical. */
 
 /*
  * Solver configuration == the YAML schema of launch/iris_sitl_traj_mpc.yaml:1-85

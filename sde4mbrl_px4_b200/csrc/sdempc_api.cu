@@ -57,7 +57,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 template <int NU, int W, int PP>
 __device__ __forceinline__ void write_x_evol(const KParams& P, const Team<PP>& tm, Warp<NU, W>& c, float* dst) {
     tm.sync();   // all particles' state tapes complete
-    if (tm.warp_in_team == 0 && dst != nullptr) {
+    if (tm.warp_in_team == 0 && tm.ls_index == 0 && dst != nullptr) {
         const int t = c.lane;
         if (t <= P.H) {
             const float invP = __fdiv_rn(1.0f, (float)PP);
@@ -83,8 +83,8 @@ __device__ __forceinline__ void write_x_evol(const KParams& P, const Team<PP>& t
     tm.sync();   // tapes may be overwritten by the next problem
 }
 
-template <int NU, int W, int PP, int G, int MODE>
-__global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
+template <int NU, int W, int PP, int G, int MODE, int LSW = 1>
+__global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
     using L = Layout<NU, W>;
     extern __shared__ __align__(128) float smem[];
     float* ws = smem;
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constan
     float* warp_base = team_base + G * P.team_stride;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int team = warp / PP, wit = warp % PP;
+    constexpr int WPT = PP * LSW;   // warps per team
+    const int team = warp / WPT, wit = (warp % WPT) % PP, ls = (warp % WPT) / PP;
 
     // ---- stage the weight image once per CTA: TMA bulk copy + mbarrier ----
     if (threadIdx.x == 0) {
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constan
     c.xref = wb + P.o_xref; c.xi = wb + P.o_xi; c.xtape = wb + P.o_xtape; c.stape = wb + P.o_stape;
     c.bufA = wb + P.o_bufA; c.bufB = wb + P.o_bufB; c.act3 = wb + P.o_act3; c.lz = wb + P.o_lz; c.red = wb + P.o_red;
     if (P.mtape_g != nullptr)
-        c.mtape = P.mtape_g + ((size_t)blockIdx.x * (G * PP) + warp) * (size_t)P.H * 2 * W;
+        c.mtape = P.mtape_g + ((size_t)blockIdx.x * (G * WPT) + warp) * (size_t)P.H * 2 * W;
     else
         c.mtape = reinterpret_cast<float2*>(wb + P.o_mtape);
     c.load_regs(P.wimg);
@@ -127,8 +128,10 @@ __global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constan
     tm.warp_in_team = wit;
     tm.bar_id = 1 + team;
     tm.scratch = team_base + team * P.team_stride;
-    tm.warp0_base = warp_base + (size_t)(team * PP) * P.ws_stride;
+    tm.warp0_base = warp_base + (size_t)(team * WPT + ls * PP) * P.ws_stride;
     tm.ws_stride = P.ws_stride;
+    tm.ls_index = ls;
+    tm.ls_bar_id = 1 + team;
 
     mbar_wait(bar, 0);
 
@@ -175,9 +178,9 @@ __global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constan
             float s = P.info[b].stepsize;
             s = s > 0.f ? s : P.init_step;
             sdempc_info inf;
-            apg_solve<NU, W, PP>(P, c, tm, x0, s, inf, P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
+            apg_solve<NU, W, PP, LSW>(P, c, tm, x0, s, inf, P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
             float* pout = P.u_plan_out + (size_t)b * n;
-            if (wit == 0) {
+            if (wit == 0 && ls == 0) {
                 for (int i = lane; i < n; i += 32) pout[i] = c.xk[i];
                 if (lane == 0) P.info_out[b] = inf;
             }
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(G* PP * 32, 1) mpc_kernel(const __grid_constan
                     __syncwarp();
                 }
                 sdempc_info inf;
-                apg_solve<NU, W, PP>(P, c, tm, x0, s, inf, nullptr);
+                apg_solve<NU, W, PP, 1>(P, c, tm, x0, s, inf, nullptr);
                 s = inf.stepsize;
                 sc = sc + inf.opt_cost;
                 sn = sn + inf.num_steps;
@@ -301,10 +304,13 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(SDEMPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+constexpr int SPEC_LSW = 4;   // sibling warps of the speculative line search: one per SM sub-partition
+
 struct KernelChoice {
     void (*solve)(KParams);
     void (*rollout)(KParams);
     void (*closed)(KParams);
+    void (*solve_spec)(KParams);   // latency mode: one problem per CTA, SPEC_LSW warps (P == 1 only)
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
     bool wreg;
@@ -317,6 +323,8 @@ static KernelChoice make_choice() {
     k.solve = mpc_kernel<NU, W, PP, G, MODE_SOLVE>;
     k.rollout = mpc_kernel<NU, W, PP, G, MODE_ROLLOUT>;
     k.closed = mpc_kernel<NU, W, PP, G, MODE_CLOSED_LOOP>;
+    k.solve_spec = nullptr;
+    if constexpr (PP == 1) k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW>;
     k.nu = NU; k.W = W; k.P = PP; k.G = G;
     k.wimg_floats = L::TOTAL; k.wsmem_floats = L::SMEM_FLOATS; k.wreg = L::WREG;
     return k;
@@ -342,7 +350,7 @@ struct sdempc_handle {
     int device = 0;
     KernelChoice kc;
     KParams kp;                       // template (config + model + layout)
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0, smem_bytes_spec = 0;
     // lazily created device state
     bool dev_ready = false;
     cudaStream_t stream = nullptr;
@@ -362,7 +370,7 @@ struct sdempc_handle {
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false;
+    bool staged_ok = false, staged_spec = false;
     float last_ms = 0.f;
 };
 
@@ -444,10 +452,11 @@ static void build_kparams(sdempc_handle* h) {
     k.o_mtape = o;
     if (tape_smem) o += H * 4 * W;
     k.ws_stride = align4(o) + 4;   // +4 floats: skew consecutive warp regions across banks
-    k.team_stride = 16;
+    k.team_stride = 32;
     const KernelChoice& kc = h->kc;
     const size_t floats = (size_t)kc.wsmem_floats + 4 + (size_t)kc.G * k.team_stride + (size_t)kc.G * kc.P * k.ws_stride;
     h->smem_bytes = floats * 4;
+    h->smem_bytes_spec = ((size_t)kc.wsmem_floats + 4 + (size_t)k.team_stride + (size_t)SPEC_LSW * k.ws_stride) * 4;
 }
 
 static int ensure_device(sdempc_handle* h) {
@@ -479,6 +488,8 @@ static int ensure_device(sdempc_handle* h) {
     for (auto fn : {h->kc.solve, h->kc.rollout, h->kc.closed}) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     }
+    if (h->kc.solve_spec)
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, h->kc.solve));
     h->regs = fa.numRegs;
@@ -491,9 +502,15 @@ static int grid_for(const sdempc_handle* h, int B) {
     return std::max(1, std::min(ctas, h->sm_count));   // one persistent CTA per SM at most
 }
 
+static bool use_spec(const sdempc_handle* h, int B) {
+    // latency regime: at most one problem per SM, or forced by the flag; bit-identical to the batched kernel
+    return h->kc.solve_spec != nullptr && h->cfg.maxls >= 1 && !(h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) &&
+           ((h->cfg.flags & SDEMPC_F_SPECULATIVE_LS) != 0 || B <= h->sm_count);
+}
+
 static int ensure_mtape(sdempc_handle* h, int grid) {
     if (h->mh.width == 32) return 0;
-    const size_t warps = (size_t)grid * h->kc.G * h->kc.P;
+    const size_t warps = (size_t)grid * std::max(h->kc.G * h->kc.P, SPEC_LSW);
     if (warps <= h->mtape_warps) return 0;
     if (h->d_mtape) cudaFree(h->d_mtape);
     h->d_mtape = nullptr;
@@ -571,7 +588,8 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     else in_bytes += a16((size_t)B * 16);
     const size_t out_bytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * sizeof(sdempc_info)) + 64;
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
-    const int grid = grid_for(h, B);
+    const bool spec = use_spec(h, B);
+    const int grid = spec ? std::min(B, h->sm_count) : grid_for(h, B);
     if ((rc = ensure_mtape(h, grid))) return rc;
     if (a->trace) {
         const size_t tb = (size_t)B * h->cfg.max_iter * SDEMPC_TRACE_W * 4;
@@ -601,14 +619,16 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
-    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid;
+    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec;
     return 0;
 }
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
-    const int threads = h->kc.G * h->kc.P * 32;
+    const bool spec = (fn == h->kc.solve_spec);
+    const int threads = spec ? SPEC_LSW * 32 : h->kc.G * h->kc.P * 32;
     void* args[] = {const_cast<KParams*>(&k)};
-    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, h->smem_bytes, h->stream));
+    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args,
+                              spec ? h->smem_bytes_spec : h->smem_bytes, h->stream));
     h->launches += 1;
     return 0;
 }
@@ -773,7 +793,7 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     for (int i = 0; i < n; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch(h, h->kc.solve, h->staged, h->last_grid);
+        int rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->kc.solve, h->staged, h->last_grid);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -797,7 +817,7 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     int rc = stage_solve(h, a);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, h->kc.solve, h->staged, h->last_grid))) return rc;
+    if ((rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->kc.solve, h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
     float t = 0.f;
@@ -910,9 +930,9 @@ int64_t sdempc_launch_count(const sdempc_t* h) { return h ? h->launches : 0; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
-    out[0] = h->kc.G * h->kc.P * 32;
-    out[1] = (int32_t)h->smem_bytes;
-    out[2] = h->kc.G;
+    out[0] = h->staged_spec ? SPEC_LSW * 32 : h->kc.G * h->kc.P * 32;
+    out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->smem_bytes);
+    out[2] = h->staged_spec ? 1 : h->kc.G;
     out[3] = h->regs;
     out[4] = h->last_grid;
     out[5] = h->sm_count;

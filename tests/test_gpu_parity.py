@@ -121,6 +121,29 @@ def test_free_running_solve(solver, O, vehicle, mode, P, iters):
     _eq(u2, uo2, "tick 2 u*"); _eq(xe2, xeo2, "tick 2 x_evol"); _eq(info2[:, :7], infoo2[:, :7], "tick 2 telemetry")
 
 
+@pytest.mark.parametrize("vehicle,width", [("iris", None), ("hexa", None), ("hexa", 32)])
+def test_latency_and_batched_kernels_agree(solver, O, vehicle, width):
+    """The latency kernel (line-search trials evaluated concurrently on 4 sibling warps, one per SM sub-partition, chosen automatically
+    when B <= #SMs) and the batched kernel (sequential line search) are both bit-identical to the oracle."""
+    ov = dict(max_iter=40, rtol=0.0, atol=0.0)
+    if width:
+        ov["width"] = width
+    B = 200   # > 148 SMs: the default choice is the batched kernel
+    outs = []
+    for mode in (dict(speculative_ls=True), dict(sequential_ls=True), dict()):
+        cfg, s, o = _pair(solver, O, vehicle, "traj", **ov, **mode)
+        pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=17)
+        u0, i0 = s.reset(B)
+        n = B if mode else 9          # the last run uses a small batch: automatic latency mode
+        u, xe, info, tr = s.solve(pr["x"][:n], u0[:n], i0[:n], xref_win=pr["xref_win"][:n], rng=pr["rng"][:n], want_trace=True)
+        outs.append((u, xe, info[:, :7], tr))
+        ki = s.kernel_info()
+        assert ki["threads_per_cta"] == (128 if ("speculative_ls" in mode or not mode) else 256)
+    uo, xeo, infoo, tro = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+    for (u, xe, info, tr), n in zip(outs, (B, B, 9)):
+        _eq(u, uo[:n], "u*"); _eq(xe, xeo[:n], "x_evol"); _eq(info, infoo[:n, :7], "telemetry"); _eq(tr, tro[:n], "trace")
+
+
 def test_early_stopping_with_yaml_tolerances(solver, O):
     """Default YAML tolerances (rtol 1e-6, atol 1e-8): per-problem iteration counts differ and still match."""
     cfg, s, o = _pair(solver, O, "iris", "pos")
