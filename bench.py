@@ -125,7 +125,7 @@ def cpu_baseline(cfg, blob, pr, budget_s: float = 12.0, chunk: int = 256) -> dic
     from oracle import oracle as O
 
     o = O.Oracle(cfg, blob, "f32")
-    cores = os.cpu_count() or 1
+    cores = O.set_threads(len(os.sched_getaffinity(0)))
     B = pr["x"].shape[0]
     u0, i0 = o.reset(min(chunk, B))
     n = min(chunk, B)
@@ -158,6 +158,7 @@ def run_reference(args, rank: int, world: int):
     from oracle import oracle as O
 
     o = O.Oracle(cfg, blob, "f32")
+    cores = O.set_threads(len(os.sched_getaffinity(0)))
     n = pr["x"].shape[0]
     u0, i0 = o.reset(n)
     kw = dict(xref_win=pr["xref_win"], rng=pr["rng"])
@@ -168,7 +169,6 @@ def run_reference(args, rank: int, world: int):
         o.solve(pr["x"], u0, i0, **kw)
     el = time.perf_counter() - t0
     v = n * args.steps / el
-    cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "batched_mpc_solves_per_sec", "value": v, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True,

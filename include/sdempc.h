@@ -201,6 +201,8 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms);
 /* D2H of the outputs of the last launch into `args` and stream synchronise. */
 int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args);
 
+/* CUDA-event duration (ms) of the most recent kernel launch of this handle, on its own stream. */
+float sdempc_last_launch_ms(const sdempc_t* h);
 /* Kernels launched by this handle so far (for bench.py's gpu_launches). */
 int64_t sdempc_launch_count(const sdempc_t* h);
 /* Static properties of the compiled solve kernel chosen for this handle:

@@ -172,6 +172,12 @@ class Oracle:
         return xh, uh, stats
 
 
+def set_threads(n: int) -> int:
+    """Number of OpenMP threads for the batched oracle calls (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().oracle_set_threads(C.c_int(int(n)))
+    return int(lib().oracle_get_max_threads())
+
+
 def philox4x32_10(ctr, key):
     ctr = np.ascontiguousarray(ctr, np.uint32)
     key = np.ascontiguousarray(key, np.uint32)

@@ -30,4 +30,14 @@
 #undef SUFFIX
 #undef REAL_IS_DOUBLE
 
+#ifdef _OPENMP
+#include <omp.h>
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must use the host cores it is given */
+void oracle_set_threads(int n) { omp_set_num_threads(n); }
+int oracle_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_get_max_threads(void) { return 1; }
+#endif
+
 const char* oracle_version(void) { return "sdempc-oracle 1 (parity unpinned: restates SURVEY.md section 8a [SPEC])"; }

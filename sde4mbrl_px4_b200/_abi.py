@@ -82,7 +82,7 @@ class SolveArgs(C.Structure):
 HEADER_SYMBOLS = [
     "sdempc_create", "sdempc_set_trajectory", "sdempc_state_from_traj", "sdempc_reset",
     "sdempc_solve_ex", "sdempc_solve", "sdempc_rollout", "sdempc_closed_loop", "sdempc_stage",
-    "sdempc_launch_timed", "sdempc_fetch", "sdempc_launch_count", "sdempc_kernel_info",
+    "sdempc_launch_timed", "sdempc_fetch", "sdempc_launch_count", "sdempc_last_launch_ms", "sdempc_kernel_info",
     "sdempc_destroy", "sdempc_last_error", "sdempc_version",
 ]
 
@@ -122,6 +122,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.sdempc_fetch.argtypes = [vp, C.POINTER(SolveArgs)]
     lib.sdempc_launch_count.argtypes = [vp]
     lib.sdempc_launch_count.restype = C.c_int64
+    lib.sdempc_last_launch_ms.argtypes = [vp]
+    lib.sdempc_last_launch_ms.restype = C.c_float
     lib.sdempc_kernel_info.argtypes = [vp, C.POINTER(_i * 6)]
     lib.sdempc_destroy.argtypes = [vp]
     lib.sdempc_destroy.restype = None

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
             float se = 0.f, me = 0.f, sc = 0.f, sn = 0.f;
             const float dt0 = P.dt[0];
             for (int k = 0; k < P.ticks; ++k, ++tick) {
-                if (P.x_hist != nullptr && wit == 0 && lane == 0) {
+                if (P.x_hist != nullptr && wit == 0 && ls == 0 && lane == 0) {
                     float o[NX];
                     if (enu) enu_ned(x0, o);
                     else {
@@ -240,13 +240,13 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
                     __syncwarp();
                 }
                 sdempc_info inf;
-                apg_solve<NU, W, PP, 1>(P, c, tm, x0, s, inf, nullptr);
+                apg_solve<NU, W, PP, LSW>(P, c, tm, x0, s, inf, nullptr);
                 s = inf.stepsize;
                 sc = sc + inf.opt_cost;
                 sn = sn + inf.num_steps;
                 float u0[NU];
                 load_u<NU>(c.xk, 0, u0);
-                if (P.u_hist != nullptr && wit == 0 && lane == 0) {
+                if (P.u_hist != nullptr && wit == 0 && ls == 0 && lane == 0) {
 #pragma unroll
                     for (int i = 0; i < NU; ++i) P.u_hist[((size_t)b * P.ticks + k) * NU + i] = u0[i];
                 }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
                 se = se + e2;
                 me = e2 > me ? e2 : me;
             }
-            if (wit == 0 && lane == 0) {
+            if (wit == 0 && ls == 0 && lane == 0) {
                 if (P.x_hist != nullptr) {
                     float o[NX];
                     if (enu) enu_ned(x0, o);
@@ -311,6 +311,7 @@ struct KernelChoice {
     void (*rollout)(KParams);
     void (*closed)(KParams);
     void (*solve_spec)(KParams);   // latency mode: one problem per CTA, SPEC_LSW warps (P == 1 only)
+    void (*closed_spec)(KParams);
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
     bool wreg;
@@ -324,7 +325,11 @@ static KernelChoice make_choice() {
     k.rollout = mpc_kernel<NU, W, PP, G, MODE_ROLLOUT>;
     k.closed = mpc_kernel<NU, W, PP, G, MODE_CLOSED_LOOP>;
     k.solve_spec = nullptr;
-    if constexpr (PP == 1) k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW>;
+    k.closed_spec = nullptr;
+    if constexpr (PP == 1) {
+        k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW>;
+        k.closed_spec = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW>;
+    }
     k.nu = NU; k.W = W; k.P = PP; k.G = G;
     k.wimg_floats = L::TOTAL; k.wsmem_floats = L::SMEM_FLOATS; k.wreg = L::WREG;
     return k;
@@ -488,8 +493,10 @@ static int ensure_device(sdempc_handle* h) {
     for (auto fn : {h->kc.solve, h->kc.rollout, h->kc.closed}) {
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     }
-    if (h->kc.solve_spec)
+    if (h->kc.solve_spec) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.closed_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
+    }
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, h->kc.solve));
     h->regs = fa.numRegs;
@@ -624,7 +631,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
 }
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
-    const bool spec = (fn == h->kc.solve_spec);
+    const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const int threads = spec ? SPEC_LSW * 32 : h->kc.G * h->kc.P * 32;
     void* args[] = {const_cast<KParams*>(&k)};
     CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args,
@@ -896,7 +903,8 @@ int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const flo
     const size_t xh = x_hist ? a16((size_t)R * (ticks + 1) * NX * 4) : 0, uh = u_hist ? a16((size_t)R * ticks * NU * 4) : 0;
     const size_t out_bytes = a16((size_t)R * 16) + xh + uh + 64;
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
-    const int grid = grid_for(h, R);
+    const bool spec = use_spec(h, R);
+    const int grid = spec ? std::min(R, h->sm_count) : grid_for(h, R);
     if ((rc = ensure_mtape(h, grid))) return rc;
     KParams k = h->kp;
     Packer pk{h->h_in, h->d_in};
@@ -912,7 +920,7 @@ int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const flo
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
     h->staged_ok = false;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, h->kc.closed, k, grid))) return rc;
+    if ((rc = launch(h, spec ? h->kc.closed_spec : h->kc.closed, k, grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->last_grid = grid;
     CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, po.off, cudaMemcpyDeviceToHost, h->stream));
@@ -927,6 +935,7 @@ int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const flo
 }
 
 int64_t sdempc_launch_count(const sdempc_t* h) { return h ? h->launches : 0; }
+float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");

@@ -144,6 +144,9 @@ class MPCSolver:
         self._check(self.lib.sdempc_fetch(self._h, C.byref(a)))
         return keep["u"], keep["xe"], keep["info"]
 
+    def last_launch_ms(self) -> float:
+        return float(self.lib.sdempc_last_launch_ms(self._h))
+
     def launch_count(self) -> int:
         return int(self.lib.sdempc_launch_count(self._h))
 
