@@ -56,8 +56,10 @@ extern "C" {
 #define SDEMPC_F_FRAME_ENU 1u      /* external frame is ENU/FLU (convert_to_enu=True, sde_control.py:685) */
 #define SDEMPC_F_NO_SHIFT 2u       /* do not shift the plan by one step at the start of a solve */
 #define SDEMPC_F_SPECULATIVE_LS 4u /* force latency mode: all line-search trials evaluated concurrently on sibling warps */
-#define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the batched kernel (sequential line search) even for small batches;
-                                      default: latency mode when B <= number of SMs.  Results are bit-identical. */
+#define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
+#define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
+/* Default kernel choice: latency kernel when B <= number of SMs, throughput kernel above (P = 1, width 32),
+ * one warp per problem otherwise.  All three produce bit-identical results. */
 
 /*
  * Solver configuration == the YAML schema of launch/iris_sitl_traj_mpc.yaml:1-85

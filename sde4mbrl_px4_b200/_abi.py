@@ -21,6 +21,7 @@ F_FRAME_ENU = 1
 F_NO_SHIFT = 2
 F_SPECULATIVE_LS = 4
 F_SEQUENTIAL_LS = 8
+F_GROUP = 16
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 

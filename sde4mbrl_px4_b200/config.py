@@ -77,6 +77,8 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
         flags |= _abi.F_SPECULATIVE_LS
     if overrides.get("sequential_ls", False):
         flags |= _abi.F_SEQUENTIAL_LS
+    if overrides.get("group", False):
+        flags |= _abi.F_GROUP
     c.flags = flags
     for t, v in enumerate(time_steps(cfg)):
         c.dt[t] = float(v)

@@ -51,7 +51,8 @@ struct KParams {
     float2* mtape_g;     // global MLP tape scratch (W = 64), per resident warp
     // per-warp shared-memory layout (float offsets), computed on the host
     int ws_stride, o_xk, o_yk, o_g, o_xp, o_uprev, o_xref, o_xi, o_xtape, o_stape, o_mtape, o_bufA, o_bufB,
-        o_act3, o_lz, o_red;
+        o_act3, o_lz, o_red, o_zb, o_lob;
+    int gx_stride;       // group kernel: floats of per-warp exchange buffers (bufA | bufB | act3)
     int team_stride;     // per-team scratch (P > 1): floats
     // batch I/O (device pointers)
     int B;
@@ -255,102 +256,32 @@ __device__ __forceinline__ void store13_lane0(float* p, const float (&x)[NX], in
 }
 
 // ---------------------------------------------------------------------------------
-// One Euler-Maruyama step + stage cost.  MODE 0: cost only; 1: record the full
-// tape for the adjoint; 2: record the state tape only (final x_evol pass).
-// x is advanced in place; returns the undiscounted stage cost (all lanes).
+// Register-level pieces of one step (no memory access), shared by the per-warp
+// kernel (state replicated in all lanes) and the group kernel (lane = problem).
 // ---------------------------------------------------------------------------------
-template <int NU, int W, int MODE>
-__device__ __forceinline__ float fwd_step(const KParams& P, Warp<NU, W>& c, int t, float disc, float (&x)[NX],
-                                          const float (&u)[NU], const float (&up)[NU]) {
-    using L = Layout<NU, W>;
-    constexpr int NIN = L::NIN, UPL = L::UPL;
-    const int lane = c.lane;
+template <int NU>
+__device__ __forceinline__ void phys_features(const float (&x)[NX], const float (&u)[NU], float (&z)[6 + NU]) {
+    const float* v = x + 3;
+    float R[3][3];
+    rotmat(x + 6, R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) z[i] = fma_(R[2][i], v[2], fma_(R[1][i], v[1], R[0][i] * v[0]));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) z[3 + i] = x[10 + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) z[6 + i] = u[i];
+}
+
+// rigid body + Euler-Maruyama update + stage cost; returns the undiscounted stage cost
+template <int NU>
+__device__ __forceinline__ float phys_step(const KParams& P, int t, const float (&x)[NX], const float (&u)[NU],
+                                           const float (&up)[NU], const float (&r)[6], const float (&sig)[6],
+                                           const float (&xi)[6], const float (&xr)[NX], float (&xn)[NX], float& rn) {
     const float* v = x + 3;
     const float* q = x + 6;
     const float* w = x + 10;
     float R[3][3];
     rotmat(q, R);
-    float z[NIN];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) z[i] = fma_(R[2][i], v[2], fma_(R[1][i], v[1], R[0][i] * v[0]));
-#pragma unroll
-    for (int i = 0; i < 3; ++i) z[3 + i] = w[i];
-#pragma unroll
-    for (int i = 0; i < NU; ++i) z[6 + i] = u[i];
-
-    float2* mt = c.mtape + (size_t)t * 2 * W;
-    // ---- layer 1: lane j, both nets ----
-#pragma unroll
-    for (int uu = 0; uu < UPL; ++uu) {
-        float2 a[4];
-        a[0] = c.B1(uu); a[1] = a[2] = a[3] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < NIN; ++k) {
-            const float2 wv = c.W1P(uu, k);
-            a[k & 3].x = fma_(wv.x, z[k], a[k & 3].x);
-            a[k & 3].y = fma_(wv.y, z[k], a[k & 3].y);
-        }
-        const float2 h = det_tanh2(add2_(add2_(a[0], a[1]), add2_(a[2], a[3])));
-        reinterpret_cast<float2*>(c.bufA)[lane + 32 * uu] = h;
-        if constexpr (MODE == 1) mt[lane + 32 * uu] = h;
-    }
-    __syncwarp();
-    // ---- layer 2 ----
-    {
-        float2 a[UPL][4];
-#pragma unroll
-        for (int uu = 0; uu < UPL; ++uu) { a[uu][0] = c.B2(uu); a[uu][1] = a[uu][2] = a[uu][3] = make_float2(0.f, 0.f); }
-#pragma unroll
-        for (int k = 0; k < W; k += 2) {
-            const float4 hv = lds4(c.bufA + 2 * k);
-#pragma unroll
-            for (int uu = 0; uu < UPL; ++uu) {
-                float2 w0, w1;
-                if constexpr (L::WREG) { w0 = c.w2[uu][k]; w1 = c.w2[uu][k + 1]; }
-                else { const float4 wv = lds4(c.ws + L::W2P + (lane + 32 * uu) * L::PAIR_STRIDE + 2 * k); w0 = xy(wv); w1 = zw(wv); }
-                a[uu][k & 3] = fma2_(w0, xy(hv), a[uu][k & 3]);
-                a[uu][(k + 1) & 3] = fma2_(w1, zw(hv), a[uu][(k + 1) & 3]);
-            }
-        }
-#pragma unroll
-        for (int uu = 0; uu < UPL; ++uu) {
-            const float2 h = det_tanh2(add2_(add2_(a[uu][0], a[uu][1]), add2_(a[uu][2], a[uu][3])));
-            c.act3[lane + 32 * uu] = h.x;
-            c.act3[W + 4 + lane + 32 * uu] = h.y;
-            if constexpr (MODE == 1) mt[W + lane + 32 * uu] = h;
-        }
-    }
-    __syncwarp();
-    // ---- output layer: lanes 0..5 drift rows, 6..11 diffusion rows ----
-    float* ob = (MODE == 1) ? (c.stape + t * 20) : c.lz;   // MODE != 1: 20-float scratch (lz has 24)
-    {
-        const int o = lane < 12 ? lane : 11;
-        const float* row = c.ws + L::W3R + o * L::W3R_STRIDE;
-        const float* src = c.act3 + (o >= 6 ? W + 4 : 0);
-        float a0 = c.ws[L::B3 + o], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < W; k += 4) {
-            const float4 wv = lds4(row + k), hv = lds4(src + k);
-            a0 = fma_(wv.x, hv.x, a0); a1 = fma_(wv.y, hv.y, a1); a2 = fma_(wv.z, hv.z, a2); a3 = fma_(wv.w, hv.w, a3);
-        }
-        const float out = (a0 + a1) + (a2 + a3);
-        float sp, sg;
-        det_softplus_sigmoid(out, sp, sg);
-        const float s0 = P.sig0[o >= 6 ? o - 6 : 0];
-        if (lane < 6) ob[lane] = out;
-        else if (lane < 12) {
-            ob[lane] = s0 * sp;
-            if constexpr (MODE == 1) ob[lane + 6] = s0 * sg;
-        }
-    }
-    __syncwarp();
-    float r[6], sig[6];
-    {
-        const float4 a = lds4(ob), b = lds4(ob + 4), d = lds4(ob + 8);
-        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y;
-        sig[0] = b.z; sig[1] = b.w; sig[2] = d.x; sig[3] = d.y; sig[4] = d.z; sig[5] = d.w;
-    }
-    // ---- rigid body ----
     float Tsum = 0.f, Mb[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) Mb[k] = P.J[k] * r[3 + k];
@@ -376,29 +307,18 @@ __device__ __forceinline__ float fwd_step(const KParams& P, Warp<NU, W>& c, int 
 #pragma unroll
     for (int i = 1; i < 6; ++i) sig2 = fma_(sig[i], sig[i], sig2);
     const float dt = P.dt[t], sdt = P.sdt[t];
-    float xi[6];
-    {
-        const float4 a = lds4(c.xi + t * 8);
-        const float2 b = lds2(c.xi + t * 8 + 4);
-        xi[0] = a.x; xi[1] = a.y; xi[2] = a.z; xi[3] = a.w; xi[4] = b.x; xi[5] = b.y;
-    }
-    float xn[NX];
 #pragma unroll
     for (int i = 0; i < 3; ++i) xn[i] = fma_(v[i], dt, x[i]);
 #pragma unroll
     for (int i = 0; i < 3; ++i) xn[3 + i] = fma_(sig[i] * xi[i], sdt, fma_(acc[i], dt, v[i]));
     const float qt0 = fma_(qd0, dt, q[0]), qt1 = fma_(qd1, dt, q[1]), qt2 = fma_(qd2, dt, q[2]), qt3 = fma_(qd3, dt, q[3]);
     const float n2 = fma_(qt3, qt3, fma_(qt2, qt2, fma_(qt1, qt1, qt0 * qt0)));
-    const float rn = det_rsqrt_near1(n2);
+    rn = det_rsqrt_near1(n2);
     xn[6] = qt0 * rn; xn[7] = qt1 * rn; xn[8] = qt2 * rn; xn[9] = qt3 * rn;
     xn[10] = fma_(sig[3] * xi[3], sdt, fma_(wd0, dt, w[0]));
     xn[11] = fma_(sig[4] * xi[4], sdt, fma_(wd1, dt, w[1]));
     xn[12] = fma_(sig[5] * xi[5], sdt, fma_(wd2, dt, w[2]));
-    if constexpr (MODE == 1) { if (lane == 0) { ob[18] = rn; ob[19] = disc; } }
-    if constexpr (MODE != 0) store13_lane0(c.xtape + (t + 1) * 16, xn, lane);
     // ---- stage cost on (x_{t+1}, u_t) ----
-    float xr[NX];
-    load13(c.xref + (t + 1) * 16, xr);
     float l = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { const float e = xn[i] - xr[i]; l = fma_(P.perr[i] * e, e, l); }
@@ -417,6 +337,155 @@ __device__ __forceinline__ float fwd_step(const KParams& P, Warp<NU, W>& c, int 
         l = fma_(P.slew * ds, ds, l);
     }
     l = fma_(P.res_mult, sig2, l);
+    return l;
+}
+
+// Both networks for NP problems at once (lane j = hidden unit j; NP independent dependency chains are
+// interleaved for instruction-level parallelism): z (replicated registers) -> ob[0..5] = residual outputs,
+// ob[6..11] = sigma, ob[12..17] = d sigma / d s (MODE 1).  mt: activation tape of each (problem, step)
+// (MODE 1).  Problem p uses the exchange buffers at c.bufA/c.act3 + p * xstride.  Ends with a __syncwarp
+// after which every ob is readable by every lane.
+// MODE < 0: whether to record the tape is the run-time flag `rec` (one copy of the code for all rollouts).
+template <int NU, int W, int MODE, int NP>
+__device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, const float (&z)[NP][6 + NU], float2* const (&mt)[NP],
+                                              float* const (&ob)[NP], int xstride, bool rec = false) {
+    using L = Layout<NU, W>;
+    constexpr int NIN = L::NIN, UPL = L::UPL;
+    const int lane = c.lane;
+    const bool tape = (MODE == 1) || (MODE < 0 && rec);
+    // ---- layer 1: lane j, both nets ----
+#pragma unroll
+    for (int uu = 0; uu < UPL; ++uu) {
+        float2 a[NP][4];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { a[p][0] = c.B1(uu); a[p][1] = a[p][2] = a[p][3] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int k = 0; k < NIN; ++k) {
+            const float2 wv = c.W1P(uu, k);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                a[p][k & 3].x = fma_(wv.x, z[p][k], a[p][k & 3].x);
+                a[p][k & 3].y = fma_(wv.y, z[p][k], a[p][k & 3].y);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float2 h = det_tanh2(add2_(add2_(a[p][0], a[p][1]), add2_(a[p][2], a[p][3])));
+            reinterpret_cast<float2*>(c.bufA + p * xstride)[lane + 32 * uu] = h;
+            if (tape) mt[p][lane + 32 * uu] = h;
+        }
+    }
+    __syncwarp();
+    // ---- layer 2 ----
+    {
+        float2 a[NP][UPL][4];
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+            for (int uu = 0; uu < UPL; ++uu) { a[p][uu][0] = c.B2(uu); a[p][uu][1] = a[p][uu][2] = a[p][uu][3] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int k = 0; k < W; k += 2) {
+            float4 hv[NP];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) hv[p] = lds4(c.bufA + p * xstride + 2 * k);
+#pragma unroll
+            for (int uu = 0; uu < UPL; ++uu) {
+                float2 w0, w1;
+                if constexpr (L::WREG) { w0 = c.w2[uu][k]; w1 = c.w2[uu][k + 1]; }
+                else { const float4 wv = lds4(c.ws + L::W2P + (lane + 32 * uu) * L::PAIR_STRIDE + 2 * k); w0 = xy(wv); w1 = zw(wv); }
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    a[p][uu][k & 3] = fma2_(w0, xy(hv[p]), a[p][uu][k & 3]);
+                    a[p][uu][(k + 1) & 3] = fma2_(w1, zw(hv[p]), a[p][uu][(k + 1) & 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p)
+#pragma unroll
+            for (int uu = 0; uu < UPL; ++uu) {
+                const float2 h = det_tanh2(add2_(add2_(a[p][uu][0], a[p][uu][1]), add2_(a[p][uu][2], a[p][uu][3])));
+                c.act3[p * xstride + lane + 32 * uu] = h.x;
+                c.act3[p * xstride + W + 4 + lane + 32 * uu] = h.y;
+                if (tape) mt[p][W + lane + 32 * uu] = h;
+            }
+    }
+    __syncwarp();
+    // ---- output layer: lanes 0..5 drift rows, 6..11 diffusion rows ----
+    {
+        const int o = lane < 12 ? lane : 11;
+        const float* row = c.ws + L::W3R + o * L::W3R_STRIDE;
+        float a0[NP], a1[NP], a2[NP], a3[NP];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) { a0[p] = c.ws[L::B3 + o]; a1[p] = a2[p] = a3[p] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < W; k += 4) {
+            const float4 wv = lds4(row + k);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float4 hv = lds4(c.act3 + p * xstride + (o >= 6 ? W + 4 : 0) + k);
+                a0[p] = fma_(wv.x, hv.x, a0[p]); a1[p] = fma_(wv.y, hv.y, a1[p]);
+                a2[p] = fma_(wv.z, hv.z, a2[p]); a3[p] = fma_(wv.w, hv.w, a3[p]);
+            }
+        }
+        const float s0 = P.sig0[o >= 6 ? o - 6 : 0];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float out = (a0[p] + a1[p]) + (a2[p] + a3[p]);
+            float sp, sg;
+            det_softplus_sigmoid(out, sp, sg);
+            if (lane < 6) ob[p][lane] = out;
+            else if (lane < 12) {
+                ob[p][lane] = s0 * sp;
+                if (tape) ob[p][lane + 6] = s0 * sg;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int NU, int W, int MODE>
+__device__ __forceinline__ void mlp_forward(const KParams& P, Warp<NU, W>& c, const float (&z)[6 + NU], float2* mt, float* ob) {
+    float z1[1][6 + NU];
+#pragma unroll
+    for (int i = 0; i < 6 + NU; ++i) z1[0][i] = z[i];
+    float2* const mt1[1] = {mt};
+    float* const ob1[1] = {ob};
+    mlp_forward_n<NU, W, MODE, 1>(P, c, z1, mt1, ob1, 0);
+}
+
+__device__ __forceinline__ void load_r_sig(const float* ob, float (&r)[6], float (&sig)[6]) {
+    const float4 a = lds4(ob), b = lds4(ob + 4), d = lds4(ob + 8);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y;
+    sig[0] = b.z; sig[1] = b.w; sig[2] = d.x; sig[3] = d.y; sig[4] = d.z; sig[5] = d.w;
+}
+
+__device__ __forceinline__ void load6(const float* p, float (&o)[6]) {
+    const float4 a = lds4(p);
+    const float2 b = lds2(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y;
+}
+
+// ---------------------------------------------------------------------------------
+// One Euler-Maruyama step + stage cost of the per-warp kernel.  MODE 0: cost only;
+// 1: record the full tape for the adjoint; 2: record the state tape only (final
+// x_evol pass).  x is advanced in place; returns the undiscounted stage cost.
+// ---------------------------------------------------------------------------------
+template <int NU, int W, int MODE>
+__device__ __forceinline__ float fwd_step(const KParams& P, Warp<NU, W>& c, int t, float disc, float (&x)[NX],
+                                          const float (&u)[NU], const float (&up)[NU]) {
+    const int lane = c.lane;
+    float z[6 + NU];
+    phys_features<NU>(x, u, z);
+    float* ob = (MODE == 1) ? (c.stape + t * 20) : c.lz;   // MODE != 1: 20-float scratch (lz has 24)
+    mlp_forward<NU, W, MODE>(P, c, z, c.mtape + (size_t)t * 2 * W, ob);
+    float r[6], sig[6], xi[6], xr[NX], xn[NX], rn;
+    load_r_sig(ob, r, sig);
+    load6(c.xi + t * 8, xi);
+    load13(c.xref + (t + 1) * 16, xr);
+    const float l = phys_step<NU>(P, t, x, u, up, r, sig, xi, xr, xn, rn);
+    if constexpr (MODE == 1) { if (lane == 0) { ob[18] = rn; ob[19] = disc; } }
+    if constexpr (MODE != 0) store13_lane0(c.xtape + (t + 1) * 16, xn, lane);
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = xn[i];
     return l;
@@ -446,13 +515,243 @@ __device__ __forceinline__ float rollout_fwd(const KParams& P, Warp<NU, W>& c, c
 }
 
 // ---------------------------------------------------------------------------------
-// Adjoint sweep (after rollout_fwd<MODE=1> at the same useq): writes this
-// particle's gradient to c.g[H][NU].
+// Adjoint of one step, in three pieces: bwd_pre (cost, normalisation, EM and rigid-body
+// adjoints down to the network outputs), mlp_backward (both networks, transposed),
+// bwd_post (feature / rotation adjoints, direct input terms).
+// ---------------------------------------------------------------------------------
+struct BwdMid {
+    float lp[3], lv[3], lw[3], lq[4], la[3], fb[3], g2;
+};
+
+// lam: dJ/dx_{t+1} WITHOUT this stage's direct cost.  Outputs: mid, lo[6] = (drift, diffusion) output adjoints,
+// gu[NU] = thrust part of dJ/du_t.
+template <int NU>
+__device__ __forceinline__ void bwd_pre(const KParams& P, int t, const float (&x)[NX], const float (&xn)[NX], const float (&xr)[NX],
+                                        const float (&u)[NU], const float (&r012)[3], const float (&sig)[6], const float (&dsg)[6],
+                                        float rn, float disc, const float (&xi)[6], float (&lam)[NX], BwdMid& m, float2 (&lo)[6],
+                                        float (&gu)[NU]) {
+    const float dt = P.dt[t], sdt = P.sdt[t];
+    const float* q = x + 6;
+    const float* w = x + 10;
+    const float g2 = 2.f * disc;
+    m.g2 = g2;
+    // direct cost on x_{t+1}
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        lam[i] = fma_(g2 * P.perr[i], xn[i] - xr[i], lam[i]);
+        lam[3 + i] = fma_(g2 * P.verr[i], xn[3 + i] - xr[3 + i], lam[3 + i]);
+        lam[10 + i] = fma_(g2 * P.werr[i], xn[10 + i] - xr[10 + i], lam[10 + i]);
+    }
+    {
+        const float* rq = xr + 6;
+        float e[3];
+        quat_err(rq, xn + 6, e);
+        const float k0 = (g2 * P.qerr[0]) * e[0], k1 = (g2 * P.qerr[1]) * e[1], k2 = (g2 * P.qerr[2]) * e[2];
+        lam[6] = lam[6] - fma_(rq[3], k2, fma_(rq[2], k1, rq[1] * k0));
+        lam[7] = lam[7] + fma_(rq[2], k2, fma_(-rq[3], k1, rq[0] * k0));
+        lam[8] = lam[8] + fma_(-rq[1], k2, fma_(rq[0], k1, rq[3] * k0));
+        lam[9] = lam[9] + fma_(rq[0], k2, fma_(rq[1], k1, (-rq[2]) * k0));
+    }
+    float lqt[4];
+    {
+        const float dot = fma_(xn[9], lam[9], fma_(xn[8], lam[8], fma_(xn[7], lam[7], xn[6] * lam[6])));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lqt[i] = fma_(-xn[6 + i], dot, lam[6 + i]) * rn;
+    }
+    float lwd[3], lsig[6];
+    const float rs2 = g2 * P.res_mult;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        m.lp[i] = lam[i];
+        m.lv[i] = fma_(dt, lam[i], lam[3 + i]);
+        m.la[i] = dt * lam[3 + i];
+        m.lw[i] = lam[10 + i];
+        lwd[i] = dt * lam[10 + i];
+        lsig[i] = fma_(rs2, sig[i], (lam[3 + i] * xi[i]) * sdt);
+        lsig[3 + i] = fma_(rs2, sig[3 + i], (lam[10 + i] * xi[3 + i]) * sdt);
+    }
+    {
+        const float l0 = dt * lqt[0], l1 = dt * lqt[1], l2 = dt * lqt[2], l3 = dt * lqt[3];
+        m.lq[0] = fma_(0.5f, fma_(w[2], l3, fma_(w[1], l2, w[0] * l1)), lqt[0]);
+        m.lq[1] = fma_(0.5f, fma_(w[1], l3, fma_(-w[2], l2, (-w[0]) * l0)), lqt[1]);
+        m.lq[2] = fma_(0.5f, fma_(-w[0], l3, fma_(w[2], l1, (-w[1]) * l0)), lqt[2]);
+        m.lq[3] = fma_(0.5f, fma_(w[0], l2, fma_(-w[1], l1, (-w[2]) * l0)), lqt[3]);
+        m.lw[0] = fma_(0.5f, fma_(-q[2], l3, fma_(q[3], l2, fma_(q[0], l1, (-q[1]) * l0))), m.lw[0]);
+        m.lw[1] = fma_(0.5f, fma_(q[1], l3, fma_(q[0], l2, fma_(-q[3], l1, (-q[2]) * l0))), m.lw[1]);
+        m.lw[2] = fma_(0.5f, fma_(q[0], l3, fma_(-q[1], l2, fma_(q[2], l1, (-q[3]) * l0))), m.lw[2]);
+    }
+    const float lMb[3] = {P.Jinv[0] * lwd[0], P.Jinv[1] * lwd[1], P.Jinv[2] * lwd[2]};
+    m.lw[0] = m.lw[0] - fma_(P.Jd[2] * w[1], lMb[2], (P.Jd[1] * w[2]) * lMb[1]);
+    m.lw[1] = m.lw[1] - fma_(P.Jd[2] * w[0], lMb[2], (P.Jd[0] * w[2]) * lMb[0]);
+    m.lw[2] = m.lw[2] - fma_(P.Jd[1] * w[0], lMb[1], (P.Jd[0] * w[1]) * lMb[0]);
+    float R[3][3];
+    rotmat(q, R);
+    float Tsum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NU; ++i) { const float T = P.kT * (u[i] * u[i]); Tsum = (i == 0) ? T : Tsum + T; }
+    m.fb[0] = r012[0]; m.fb[1] = r012[1]; m.fb[2] = fma_(-Tsum, P.inv_m, r012[2]);
+    float lfb[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) lfb[j] = fma_(R[2][j], m.la[2], fma_(R[1][j], m.la[1], R[0][j] * m.la[0]));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k].x = lfb[k]; lo[3 + k].x = P.J[k] * lMb[k]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) lo[i].y = lsig[i] * dsg[i];
+    const float lTsum = -(lfb[2] * P.inv_m);
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+        const float lT = fma_(P.mixer[2][i], lMb[2], fma_(P.mixer[1][i], lMb[1], fma_(P.mixer[0][i], lMb[0], lTsum)));
+        gu[i] = (P.kT2 * u[i]) * lT;
+    }
+}
+
+// lz[NIN] (feature adjoints) -> lzbuf (shared) for NP problems at once; lo replicated in registers; mt =
+// activation tape of each (problem, step); problem p uses c.bufA/c.bufB + p * xstride.  Ends with a
+// __syncwarp after which every lzbuf is readable by every lane.
+template <int NU, int W, int NP>
+__device__ __forceinline__ void mlp_backward_n(Warp<NU, W>& c, const float2 (&lo)[NP][6], const float2* const (&mt)[NP],
+                                               float* const (&lzbuf)[NP], int xstride) {
+    using L = Layout<NU, W>;
+    constexpr int NIN = L::NIN, UPL = L::UPL;
+    const int lane = c.lane;
+    const float2 one = make_float2(1.f, 1.f);
+#pragma unroll
+    for (int uu = 0; uu < UPL; ++uu) {
+        float2 w3[6];
+#pragma unroll
+        for (int o = 0; o < 6; ++o) w3[o] = c.W3C(uu, o);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float2 a0 = fma2_(w3[0], lo[p][0], make_float2(0.f, 0.f));
+            float2 a1 = fma2_(w3[1], lo[p][1], make_float2(0.f, 0.f));
+            const float2 a2 = fma2_(w3[2], lo[p][2], make_float2(0.f, 0.f));
+            const float2 a3 = fma2_(w3[3], lo[p][3], make_float2(0.f, 0.f));
+            a0 = fma2_(w3[4], lo[p][4], a0);
+            a1 = fma2_(w3[5], lo[p][5], a1);
+            const float2 h = mt[p][W + lane + 32 * uu];
+            const float2 d = mul2_(add2_(add2_(a0, a1), add2_(a2, a3)), fma2_(make_float2(-h.x, -h.y), h, one));
+            reinterpret_cast<float2*>(c.bufA + p * xstride)[lane + 32 * uu] = d;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int uu = 0; uu < UPL; ++uu) {
+        const float* row = c.ws + L::W2T + (lane + 32 * uu) * L::PAIR_STRIDE;
+        float2 a[NP][4];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) a[p][0] = a[p][1] = a[p][2] = a[p][3] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            const float4 wv = lds4(row + 2 * j);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float4 dv = lds4(c.bufA + p * xstride + 2 * j);
+                a[p][j & 3] = fma2_(xy(wv), xy(dv), a[p][j & 3]);
+                a[p][(j + 1) & 3] = fma2_(zw(wv), zw(dv), a[p][(j + 1) & 3]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float2 h = mt[p][lane + 32 * uu];
+            const float2 d = mul2_(add2_(add2_(a[p][0], a[p][1]), add2_(a[p][2], a[p][3])), fma2_(make_float2(-h.x, -h.y), h, one));
+            reinterpret_cast<float2*>(c.bufB + p * xstride)[lane + 32 * uu] = d;
+        }
+    }
+    __syncwarp();
+    {
+        const int i = lane < NIN ? lane : NIN - 1;
+        const float* row = c.ws + L::W1T + i * L::PAIR_STRIDE;
+        float2 a[NP][4];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) a[p][0] = a[p][1] = a[p][2] = a[p][3] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            const float4 wv = lds4(row + 2 * j);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float4 dv = lds4(c.bufB + p * xstride + 2 * j);
+                a[p][j & 3] = fma2_(xy(wv), xy(dv), a[p][j & 3]);
+                a[p][(j + 1) & 3] = fma2_(zw(wv), zw(dv), a[p][(j + 1) & 3]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const float2 s = add2_(add2_(a[p][0], a[p][1]), add2_(a[p][2], a[p][3]));
+            if (lane < NIN) lzbuf[p][lane] = s.x + s.y;
+        }
+    }
+    __syncwarp();
+}
+
+template <int NU, int W>
+__device__ __forceinline__ void mlp_backward(Warp<NU, W>& c, const float2 (&lo)[6], const float2* mt, float* lzbuf) {
+    float2 lo1[1][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) lo1[0][i] = lo[i];
+    const float2* const mt1[1] = {mt};
+    float* const lz1[1] = {lzbuf};
+    mlp_backward_n<NU, W, 1>(c, lo1, mt1, lz1, 0);
+}
+
+// gp: slew term of step t+1 w.r.t. u_t on entry, of step t w.r.t. u_{t-1} on exit; gu: dJ/du_t on exit.
+template <int NU>
+__device__ __forceinline__ void bwd_post(const KParams& P, const float (&x)[NX], const float (&u)[NU], const float (&up)[NU],
+                                         BwdMid& m, const float (&lz)[6 + NU], float (&gu)[NU], float (&gp)[NU], float (&lam)[NX]) {
+    const float* v = x + 3;
+    const float* q = x + 6;
+    float R[3][3];
+    rotmat(q, R);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m.lw[i] = m.lw[i] + lz[3 + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) gu[i] = gu[i] + lz[6 + i];
+    {
+        float M[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) M[i][j] = fma_(v[i], lz[j], m.la[i] * m.fb[j]);
+        const float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
+        const float m2x = -2.f * qx, m2y = -2.f * qy, m2z = -2.f * qz;
+        const float d0 = fma_(qx, M[2][1], fma_(-qy, M[2][0], fma_(-qx, M[1][2], fma_(qz, M[1][0], fma_(qy, M[0][2], (-qz) * M[0][1])))));
+        const float d1 = fma_(m2x, M[2][2], fma_(qw, M[2][1], fma_(qz, M[2][0], fma_(-qw, M[1][2], fma_(m2x, M[1][1], fma_(qy, M[1][0], fma_(qz, M[0][2], qy * M[0][1])))))));
+        const float d2 = fma_(m2y, M[2][2], fma_(qz, M[2][1], fma_(-qw, M[2][0], fma_(qz, M[1][2], fma_(qx, M[1][0], fma_(qw, M[0][2], fma_(qx, M[0][1], m2y * M[0][0])))))));
+        const float d3 = fma_(qy, M[2][1], fma_(qx, M[2][0], fma_(qy, M[1][2], fma_(m2z, M[1][1], fma_(qw, M[1][0], fma_(qx, M[0][2], fma_(-qw, M[0][1], m2z * M[0][0])))))));
+        m.lq[0] = fma_(2.f, d0, m.lq[0]); m.lq[1] = fma_(2.f, d1, m.lq[1]);
+        m.lq[2] = fma_(2.f, d2, m.lq[2]); m.lq[3] = fma_(2.f, d3, m.lq[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m.lv[i] = fma_(R[i][2], lz[2], fma_(R[i][1], lz[1], fma_(R[i][0], lz[0], m.lv[i])));
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+        const float ds = (m.g2 * P.slew) * (u[i] - up[i]);
+        gu[i] = fma_(m.g2 * P.uerr, u[i] - P.uref[i], gu[i]) + ds;
+        const float gt = gu[i] + gp[i];
+        gp[i] = -ds;
+        gu[i] = gt;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { lam[i] = m.lp[i]; lam[3 + i] = m.lv[i]; lam[10 + i] = m.lw[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lam[6 + i] = m.lq[i];
+}
+
+// per-step tape fields written by the forward pass (MODE 1)
+__device__ __forceinline__ void load_step_tape(const float* ob, float (&r012)[3], float (&sig)[6], float (&dsg)[6], float& rn, float& disc) {
+    const float4 a = lds4(ob), b = lds4(ob + 4), d = lds4(ob + 8), e = lds4(ob + 12), f = lds4(ob + 16);
+    r012[0] = a.x; r012[1] = a.y; r012[2] = a.z;
+    sig[0] = b.z; sig[1] = b.w; sig[2] = d.x; sig[3] = d.y; sig[4] = d.z; sig[5] = d.w;
+    dsg[0] = e.x; dsg[1] = e.y; dsg[2] = e.z; dsg[3] = e.w; dsg[4] = f.x; dsg[5] = f.y;
+    rn = f.z; disc = f.w;
+}
+
+// ---------------------------------------------------------------------------------
+// Adjoint sweep of the per-warp kernel (after rollout_fwd<MODE=1> at the same useq):
+// writes this particle's gradient to c.g[H][NU].
 // ---------------------------------------------------------------------------------
 template <int NU, int W>
 __device__ __forceinline__ void rollout_bwd(const KParams& P, Warp<NU, W>& c, const float* useq) {
-    using L = Layout<NU, W>;
-    constexpr int NIN = L::NIN, UPL = L::UPL;
+    constexpr int NIN = 6 + NU;
     const int lane = c.lane;
     float lam[NX];
 #pragma unroll
@@ -470,183 +769,22 @@ __device__ __forceinline__ void rollout_bwd(const KParams& P, Warp<NU, W>& c, co
 #pragma unroll
             for (int i = 0; i < NU; ++i) up[i] = c.uprev[i];
         } else load_u<NU>(useq, t - 1, up);
-        const float* ob = c.stape + t * 20;
-        float r012[3], sig[6], dsg[6], rn, disc;
-        {
-            const float4 a = lds4(ob), b = lds4(ob + 4), d = lds4(ob + 8), e = lds4(ob + 12), f = lds4(ob + 16);
-            r012[0] = a.x; r012[1] = a.y; r012[2] = a.z;
-            sig[0] = b.z; sig[1] = b.w; sig[2] = d.x; sig[3] = d.y; sig[4] = d.z; sig[5] = d.w;
-            dsg[0] = e.x; dsg[1] = e.y; dsg[2] = e.z; dsg[3] = e.w; dsg[4] = f.x; dsg[5] = f.y;
-            rn = f.z; disc = f.w;
-        }
-        float xi[6];
-        {
-            const float4 a = lds4(c.xi + t * 8);
-            const float2 b = lds2(c.xi + t * 8 + 4);
-            xi[0] = a.x; xi[1] = a.y; xi[2] = a.z; xi[3] = a.w; xi[4] = b.x; xi[5] = b.y;
-        }
-        const float dt = P.dt[t], sdt = P.sdt[t];
-        const float* v = x + 3;
-        const float* q = x + 6;
-        const float* w = x + 10;
-        const float g2 = 2.f * disc;
-        // direct cost on x_{t+1}
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            lam[i] = fma_(g2 * P.perr[i], xn[i] - xr[i], lam[i]);
-            lam[3 + i] = fma_(g2 * P.verr[i], xn[3 + i] - xr[3 + i], lam[3 + i]);
-            lam[10 + i] = fma_(g2 * P.werr[i], xn[10 + i] - xr[10 + i], lam[10 + i]);
-        }
-        {
-            const float* rq = xr + 6;
-            float e[3];
-            quat_err(rq, xn + 6, e);
-            const float k0 = (g2 * P.qerr[0]) * e[0], k1 = (g2 * P.qerr[1]) * e[1], k2 = (g2 * P.qerr[2]) * e[2];
-            lam[6] = lam[6] - fma_(rq[3], k2, fma_(rq[2], k1, rq[1] * k0));
-            lam[7] = lam[7] + fma_(rq[2], k2, fma_(-rq[3], k1, rq[0] * k0));
-            lam[8] = lam[8] + fma_(-rq[1], k2, fma_(rq[0], k1, rq[3] * k0));
-            lam[9] = lam[9] + fma_(rq[0], k2, fma_(rq[1], k1, (-rq[2]) * k0));
-        }
-        float lqt[4];
-        {
-            const float dot = fma_(xn[9], lam[9], fma_(xn[8], lam[8], fma_(xn[7], lam[7], xn[6] * lam[6])));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lqt[i] = fma_(-xn[6 + i], dot, lam[6 + i]) * rn;
-        }
-        float lp[3], lv[3], lw[3], lq[4], la[3], lwd[3], lsig[6];
-        const float rs2 = g2 * P.res_mult;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            lp[i] = lam[i];
-            lv[i] = fma_(dt, lam[i], lam[3 + i]);
-            la[i] = dt * lam[3 + i];
-            lw[i] = lam[10 + i];
-            lwd[i] = dt * lam[10 + i];
-            lsig[i] = fma_(rs2, sig[i], (lam[3 + i] * xi[i]) * sdt);
-            lsig[3 + i] = fma_(rs2, sig[3 + i], (lam[10 + i] * xi[3 + i]) * sdt);
-        }
-        {
-            const float l0 = dt * lqt[0], l1 = dt * lqt[1], l2 = dt * lqt[2], l3 = dt * lqt[3];
-            lq[0] = fma_(0.5f, fma_(w[2], l3, fma_(w[1], l2, w[0] * l1)), lqt[0]);
-            lq[1] = fma_(0.5f, fma_(w[1], l3, fma_(-w[2], l2, (-w[0]) * l0)), lqt[1]);
-            lq[2] = fma_(0.5f, fma_(-w[0], l3, fma_(w[2], l1, (-w[1]) * l0)), lqt[2]);
-            lq[3] = fma_(0.5f, fma_(w[0], l2, fma_(-w[1], l1, (-w[2]) * l0)), lqt[3]);
-            lw[0] = fma_(0.5f, fma_(-q[2], l3, fma_(q[3], l2, fma_(q[0], l1, (-q[1]) * l0))), lw[0]);
-            lw[1] = fma_(0.5f, fma_(q[1], l3, fma_(q[0], l2, fma_(-q[3], l1, (-q[2]) * l0))), lw[1]);
-            lw[2] = fma_(0.5f, fma_(q[0], l3, fma_(-q[1], l2, fma_(q[2], l1, (-q[3]) * l0))), lw[2]);
-        }
-        const float lMb[3] = {P.Jinv[0] * lwd[0], P.Jinv[1] * lwd[1], P.Jinv[2] * lwd[2]};
-        lw[0] = lw[0] - fma_(P.Jd[2] * w[1], lMb[2], (P.Jd[1] * w[2]) * lMb[1]);
-        lw[1] = lw[1] - fma_(P.Jd[2] * w[0], lMb[2], (P.Jd[0] * w[2]) * lMb[0]);
-        lw[2] = lw[2] - fma_(P.Jd[1] * w[0], lMb[1], (P.Jd[0] * w[1]) * lMb[0]);
-        float R[3][3];
-        rotmat(q, R);
-        float Tsum = 0.f;
-#pragma unroll
-        for (int i = 0; i < NU; ++i) { const float T = P.kT * (u[i] * u[i]); Tsum = (i == 0) ? T : Tsum + T; }
-        const float fb[3] = {r012[0], r012[1], fma_(-Tsum, P.inv_m, r012[2])};
-        float lfb[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) lfb[j] = fma_(R[2][j], la[2], fma_(R[1][j], la[1], R[0][j] * la[0]));
-        float2 lo[6];   // (drift, diffusion) output adjoints
-#pragma unroll
-        for (int k = 0; k < 3; ++k) { lo[k].x = lfb[k]; lo[3 + k].x = P.J[k] * lMb[k]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) lo[i].y = lsig[i] * dsg[i];
-        const float lTsum = -(lfb[2] * P.inv_m);
+        float r012[3], sig[6], dsg[6], rn, disc, xi[6];
+        load_step_tape(c.stape + t * 20, r012, sig, dsg, rn, disc);
+        load6(c.xi + t * 8, xi);
+        BwdMid mid;
+        float2 lo[6];
         float gu[NU];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            const float lT = fma_(P.mixer[2][i], lMb[2], fma_(P.mixer[1][i], lMb[1], fma_(P.mixer[0][i], lMb[0], lTsum)));
-            gu[i] = (P.kT2 * u[i]) * lT;
-        }
-        // ---- MLP adjoint ----
-        const float2* mt = c.mtape + (size_t)t * 2 * W;
-        const float2 one = make_float2(1.f, 1.f);
-#pragma unroll
-        for (int uu = 0; uu < UPL; ++uu) {
-            float2 a0 = fma2_(c.W3C(uu, 0), lo[0], make_float2(0.f, 0.f));
-            float2 a1 = fma2_(c.W3C(uu, 1), lo[1], make_float2(0.f, 0.f));
-            const float2 a2 = fma2_(c.W3C(uu, 2), lo[2], make_float2(0.f, 0.f));
-            const float2 a3 = fma2_(c.W3C(uu, 3), lo[3], make_float2(0.f, 0.f));
-            a0 = fma2_(c.W3C(uu, 4), lo[4], a0);
-            a1 = fma2_(c.W3C(uu, 5), lo[5], a1);
-            const float2 h = mt[W + lane + 32 * uu];
-            const float2 d = mul2_(add2_(add2_(a0, a1), add2_(a2, a3)), fma2_(make_float2(-h.x, -h.y), h, one));
-            reinterpret_cast<float2*>(c.bufA)[lane + 32 * uu] = d;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int uu = 0; uu < UPL; ++uu) {
-            const float* row = c.ws + L::W2T + (lane + 32 * uu) * L::PAIR_STRIDE;
-            float2 a[4];
-            a[0] = a[1] = a[2] = a[3] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < W; j += 2) {
-                const float4 wv = lds4(row + 2 * j), dv = lds4(c.bufA + 2 * j);
-                a[j & 3] = fma2_(xy(wv), xy(dv), a[j & 3]);
-                a[(j + 1) & 3] = fma2_(zw(wv), zw(dv), a[(j + 1) & 3]);
-            }
-            const float2 h = mt[lane + 32 * uu];
-            const float2 d = mul2_(add2_(add2_(a[0], a[1]), add2_(a[2], a[3])), fma2_(make_float2(-h.x, -h.y), h, one));
-            reinterpret_cast<float2*>(c.bufB)[lane + 32 * uu] = d;
-        }
-        __syncwarp();
-        {
-            const int i = lane < NIN ? lane : NIN - 1;
-            const float* row = c.ws + L::W1T + i * L::PAIR_STRIDE;
-            float2 a[4];
-            a[0] = a[1] = a[2] = a[3] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < W; j += 2) {
-                const float4 wv = lds4(row + 2 * j), dv = lds4(c.bufB + 2 * j);
-                a[j & 3] = fma2_(xy(wv), xy(dv), a[j & 3]);
-                a[(j + 1) & 3] = fma2_(zw(wv), zw(dv), a[(j + 1) & 3]);
-            }
-            const float2 s = add2_(add2_(a[0], a[1]), add2_(a[2], a[3]));
-            if (lane < NIN) c.lz[lane] = s.x + s.y;
-        }
-        __syncwarp();
+        bwd_pre<NU>(P, t, x, xn, xr, u, r012, sig, dsg, rn, disc, xi, lam, mid, lo, gu);
+        mlp_backward<NU, W>(c, lo, c.mtape + (size_t)t * 2 * W, c.lz);
         float lz[NIN];
 #pragma unroll
         for (int i = 0; i < NIN; i += 2) { const float2 a = lds2(c.lz + i); lz[i] = a.x; lz[i + 1] = a.y; }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) lw[i] = lw[i] + lz[3 + i];
-#pragma unroll
-        for (int i = 0; i < NU; ++i) gu[i] = gu[i] + lz[6 + i];
-        {
-            float M[3][3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) M[i][j] = fma_(v[i], lz[j], la[i] * fb[j]);
-            const float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
-            const float m2x = -2.f * qx, m2y = -2.f * qy, m2z = -2.f * qz;
-            const float d0 = fma_(qx, M[2][1], fma_(-qy, M[2][0], fma_(-qx, M[1][2], fma_(qz, M[1][0], fma_(qy, M[0][2], (-qz) * M[0][1])))));
-            const float d1 = fma_(m2x, M[2][2], fma_(qw, M[2][1], fma_(qz, M[2][0], fma_(-qw, M[1][2], fma_(m2x, M[1][1], fma_(qy, M[1][0], fma_(qz, M[0][2], qy * M[0][1])))))));
-            const float d2 = fma_(m2y, M[2][2], fma_(qz, M[2][1], fma_(-qw, M[2][0], fma_(qz, M[1][2], fma_(qx, M[1][0], fma_(qw, M[0][2], fma_(qx, M[0][1], m2y * M[0][0])))))));
-            const float d3 = fma_(qy, M[2][1], fma_(qx, M[2][0], fma_(qy, M[1][2], fma_(m2z, M[1][1], fma_(qw, M[1][0], fma_(qx, M[0][2], fma_(-qw, M[0][1], m2z * M[0][0])))))));
-            lq[0] = fma_(2.f, d0, lq[0]); lq[1] = fma_(2.f, d1, lq[1]);
-            lq[2] = fma_(2.f, d2, lq[2]); lq[3] = fma_(2.f, d3, lq[3]);
-        }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) lv[i] = fma_(R[i][2], lz[2], fma_(R[i][1], lz[1], fma_(R[i][0], lz[0], lv[i])));
-#pragma unroll
-        for (int i = 0; i < NU; ++i) {
-            const float ds = (g2 * P.slew) * (u[i] - up[i]);
-            gu[i] = fma_(g2 * P.uerr, u[i] - P.uref[i], gu[i]) + ds;
-            const float gt = gu[i] + gp[i];
-            gp[i] = -ds;
-            gu[i] = gt;
-        }
+        bwd_post<NU>(P, x, u, up, mid, lz, gu, gp, lam);
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i < NU; ++i) c.g[t * NU + i] = gu[i];
         }
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { lam[i] = lp[i]; lam[3 + i] = lv[i]; lam[10 + i] = lw[i]; }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) lam[6 + i] = lq[i];
     }
     __syncwarp();
 }
@@ -856,10 +994,9 @@ __device__ __forceinline__ void apg_solve(const KParams& P, Warp<NU, W>& c, cons
 }
 
 // Philox noise of this warp's particle for one solve: xi[t][0..5], t < H (lane t)
-template <int NU, int W>
-__device__ __forceinline__ void gen_noise(const KParams& P, Warp<NU, W>& c, unsigned long long seed, unsigned long long tick,
+__device__ __forceinline__ void gen_noise(int lane, unsigned long long seed, unsigned long long tick,
                                           uint32_t particle, uint32_t sub0, int H, float* dst /*[H][8]*/) {
-    const int t = c.lane;
+    const int t = lane;
     if (t < H) {
         const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
         const uint32_t c2 = (uint32_t)tick, c3 = ((uint32_t)(tick >> 32)) & 0x3FFFFFFFu;
@@ -876,10 +1013,9 @@ __device__ __forceinline__ void gen_noise(const KParams& P, Warp<NU, W>& c, unsi
 }
 
 // Reference window into c.xref[(H+1)][16] (internal frame); lane t builds row t.
-template <int NU, int W>
-__device__ __forceinline__ void build_window(const KParams& P, Warp<NU, W>& c, const float* xref_win_b, const float* curr_t_b,
-                                             const float* xdes_b, float t_override, bool use_override) {
-    const int t = c.lane;
+__device__ __forceinline__ void build_window(const KParams& P, int lane, float* xref_dst, const float* xref_win_b,
+                                             const float* curr_t_b, const float* xdes_b, float t_override, bool use_override) {
+    const int t = lane;
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
     if (t <= P.H) {
         float row[NX];
@@ -907,7 +1043,7 @@ __device__ __forceinline__ void build_window(const KParams& P, Warp<NU, W>& c, c
             }
         }
 #pragma unroll
-        for (int i = 0; i < NX; ++i) c.xref[t * 16 + i] = row[i];
+        for (int i = 0; i < NX; ++i) xref_dst[t * 16 + i] = row[i];
     }
 }
 

