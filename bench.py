@@ -261,20 +261,27 @@ def main():
     h2d = pr["x"].nbytes + u0.nbytes + i0.nbytes + pr["xref_win"].nbytes + pr["rng"].nbytes
     d2h = u.nbytes + xe.nbytes + info.nbytes
     for _ in range(2):
-        s.solve(pr["x"], u0, i0, **kw)
+        if dist is None:
+            s.solve(pr["x"], u0, i0, **kw)
+        else:
+            sharding.solve_sharded(s, pr, u0, i0, world * B)
     barrier()
     sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ue, xee, infoe, _ = s.solve(pr["x"], u0, i0, **kw)
-        if dist is not None:   # final result gather to rank 0 (the only collective)
-            sharding.gather_results({"u": ue, "x_evol": xee, "info": infoe}, world * B, device="cuda")
+        if dist is None:
+            ue, xee, infoe, _ = s.solve(pr["x"], u0, i0, **kw)
+        else:   # H2D + solve + device-to-device result gather to rank 0 (the only collective) + one D2H there
+            g = sharding.solve_sharded(s, pr, u0, i0, world * B)
+            if rank == 0:
+                ue = g["u"][:B]
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop()
     launches_e2e = args.steps
     e2e_value = world * B * args.steps / e2e_s
-    assert np.array_equal(ue, u), "e2e solve and staged solve disagree"
+    if rank == 0:
+        assert np.array_equal(ue, u), "e2e solve and staged solve disagree"
 
     # ---------------- single-tick latency (BASELINE config 2), rank 0 only ----------------
     latency = None
@@ -307,6 +314,9 @@ def main():
                    "device": {"p50": pc(dev_l, 50), "p99": pc(dev_l, 99), "max": float(np.max(dev_l))}}
 
     # ---------------- roofline of the dominant (only) kernel ----------------
+    ki = s.kernel_info()
+    kernel_name = ("mpc_group_kernel<4,32,GP=4,GW=8>" if ki["problems_per_cta"] == 32 else
+                   "mpc_kernel<4,32,1,G=%d,SOLVE>" % ki["problems_per_cta"])
     pk = peaks()
     flops_launch = algorithmic_flops(info, H, P, F_STEP["iris"])
     achieved_tf = flops_launch / (kern_ms * 1e-3) / 1e12
@@ -314,7 +324,7 @@ def main():
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
                 "frac": achieved_tf / pk["fp32_tflops"], "traffic": None,
                 "peak_source": f"148 SM x 128 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} clock; MEASURED_PEAKS.json has no FP32-pipe figure)",
-                "kernel": "mpc_kernel<4,32,1,G,SOLVE>", "avg_launch_ms": kern_ms, "algorithmic_flop_per_launch": flops_launch,
+                "kernel": kernel_name, "avg_launch_ms": kern_ms, "algorithmic_flop_per_launch": flops_launch,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,
                         "peak_gbs": pk["hbm_gbs"], "note": "not HBM bound: ~3 KB per problem"},
                 "mean_linesearch_trials": float(info[:, 0].mean())}

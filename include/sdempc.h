@@ -200,6 +200,12 @@ int sdempc_stage(sdempc_t* h, const sdempc_solve_args* args);
  * before each launch.  ms[n] receives the CUDA-event time of each launch,
  * measured on the launching stream. */
 int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms);
+/* Wait for the handle's stream to drain. */
+int sdempc_sync(sdempc_t* h);
+/* Device address and size of the OUT block of the staged solve: x_evol[B][H+1][13] | u_plan[B][H][nu] |
+ * info[B], each sub-array 16-byte aligned, valid until the next stage/solve on this handle.  For callers that
+ * forward results device-to-device (the multi-GPU result gather) instead of through host memory. */
+int sdempc_device_out(sdempc_t* h, void** dev_ptr, size_t* nbytes);
 /* D2H of the outputs of the last launch into `args` and stream synchronise. */
 int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args);
 

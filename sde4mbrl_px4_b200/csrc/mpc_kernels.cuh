@@ -415,23 +415,24 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
     {
         const int o = lane < 12 ? lane : 11;
         const float* row = c.ws + L::W3R + o * L::W3R_STRIDE;
-        float a0[NP], a1[NP], a2[NP], a3[NP];
+        // the four partial sums of SPEC-ARITH packed two per FFMA2: (a0, a1) and (a2, a3)
+        float2 aA[NP], aB[NP];
 #pragma unroll
-        for (int p = 0; p < NP; ++p) { a0[p] = c.ws[L::B3 + o]; a1[p] = a2[p] = a3[p] = 0.f; }
+        for (int p = 0; p < NP; ++p) { aA[p] = make_float2(c.ws[L::B3 + o], 0.f); aB[p] = make_float2(0.f, 0.f); }
 #pragma unroll
         for (int k = 0; k < W; k += 4) {
             const float4 wv = lds4(row + k);
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 const float4 hv = lds4(c.act3 + p * xstride + (o >= 6 ? W + 4 : 0) + k);
-                a0[p] = fma_(wv.x, hv.x, a0[p]); a1[p] = fma_(wv.y, hv.y, a1[p]);
-                a2[p] = fma_(wv.z, hv.z, a2[p]); a3[p] = fma_(wv.w, hv.w, a3[p]);
+                aA[p] = fma2_(xy(wv), xy(hv), aA[p]);
+                aB[p] = fma2_(zw(wv), zw(hv), aB[p]);
             }
         }
         const float s0 = P.sig0[o >= 6 ? o - 6 : 0];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-            const float out = (a0[p] + a1[p]) + (a2[p] + a3[p]);
+            const float out = (aA[p].x + aA[p].y) + (aB[p].x + aB[p].y);
             float sp, sg;
             det_softplus_sigmoid(out, sp, sg);
             if (lane < 6) ob[p][lane] = out;

@@ -977,6 +977,23 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     return 0;
 }
 
+int sdempc_sync(sdempc_t* h) {
+    if (!h || !h->dev_ready) return fail(SDEMPC_ESTATE, "no device state yet");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sdempc_device_out(sdempc_t* h, void** dev_ptr, size_t* nbytes) {
+    if (!h || !dev_ptr || !nbytes) return fail(SDEMPC_EINVAL, "null argument");
+    if (!h->staged_ok) return fail(SDEMPC_ESTATE, "sdempc_stage() first");
+    const int B = h->staged_B, H = h->cfg.horizon, NU = h->cfg.nu;
+    *dev_ptr = h->d_out;
+    *nbytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * H * NU * 4) + a16((size_t)B * sizeof(sdempc_info));
+    return 0;
+}
+
 int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args) {
     if (!h || !args) return fail(SDEMPC_EINVAL, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));

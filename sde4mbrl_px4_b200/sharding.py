@@ -54,3 +54,42 @@ def gather_results(local: dict, B: int, device=None) -> dict | None:
         res[k] = allf[:, off: off + w].reshape((B,) + tuple(s))
         off += w
     return res
+
+
+class _DevBuf:
+    """Zero-copy view of a raw device allocation for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
+    """One batched solve of this rank's shard followed by the final result gather **device to device**:
+    inputs go host -> HBM (pinned staging), the solve kernel runs, every rank's OUT block (x_evol | plan |
+    telemetry) is gathered to rank 0 over NCCL / NVLink straight from the library's device buffer, and rank 0
+    copies the gathered block to the host once.  Returns the dict of [B_total, ...] arrays on rank 0, else None.
+    This is the only collective of the path."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    solver.stage(local_problem["x"], u0, info0, xref_win=local_problem.get("xref_win"), rng=local_problem.get("rng"),
+                 curr_t=local_problem.get("curr_t"), xdes=local_problem.get("xdes"))
+    solver.launch_timed(1, flush_l2=False)          # launch + event wait on the handle's stream
+    ptr, nbytes, layout = solver.device_out()
+    local = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
+    sizes = [shard_range(B_total, r, world)[1] - shard_range(B_total, r, world)[0] for r in range(world)]
+    if len(set(sizes)) != 1:
+        raise ValueError("solve_sharded needs equal shards (B_total divisible by the world size)")
+    out = torch.empty((world, local.numel()), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, local)            # ~1.5 KB per problem over NVLink
+    if rank != 0:
+        torch.cuda.current_stream().synchronize()
+        return None
+    host = out.cpu().numpy()                           # one D2H of the gathered block
+    res = {}
+    for k, (off, shape) in layout.items():
+        n = int(np.prod(shape))
+        res[k] = np.concatenate([host[r, off // 4: off // 4 + n].reshape(shape) for r in range(world)], axis=0)
+    return res

@@ -144,6 +144,21 @@ class MPCSolver:
         self._check(self.lib.sdempc_fetch(self._h, C.byref(a)))
         return keep["u"], keep["xe"], keep["info"]
 
+    def sync(self):
+        self._check(self.lib.sdempc_sync(self._h))
+
+    def device_out(self):
+        """(device pointer, nbytes, layout) of the OUT block of the staged solve; layout maps
+        name -> (byte offset, shape) of x_evol / u / info inside the block."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.sdempc_device_out(self._h, C.byref(ptr), C.byref(n)))
+        B = self._staged[1]["x"].shape[0]
+        a16 = lambda b: (b + 15) & ~15
+        o_p = a16(B * (self.H + 1) * 13 * 4)
+        o_i = o_p + a16(B * self.H * self.nu * 4)
+        layout = {"x_evol": (0, (B, self.H + 1, 13)), "u": (o_p, (B, self.H, self.nu)), "info": (o_i, (B, 8))}
+        return int(ptr.value), int(n.value), layout
+
     def last_launch_ms(self) -> float:
         return float(self.lib.sdempc_last_launch_ms(self._h))
 

@@ -79,8 +79,9 @@ def test_rollout_value_and_grad(solver, O, vehicle, P, width, enu):
     assert g2 is None
 
 
-def test_reference_modes_trajectory_table_and_setpoint(solver, O):
-    cfg, s, o = _pair(solver, O, "iris", "traj")
+@pytest.mark.parametrize("mode", [{}, {"group": True}, {"sequential_ls": True}])
+def test_reference_modes_trajectory_table_and_setpoint(solver, O, mode):
+    cfg, s, o = _pair(solver, O, "iris", "traj", max_iter=12, **mode)
     tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.7, duration=12.0))
     s.set_trajectory(tab); o.set_trajectory(tab)
     t = np.array([-1, 0, 0.013, 3.3, 11.99, 12, 40], np.float32)
@@ -93,10 +94,15 @@ def test_reference_modes_trajectory_table_and_setpoint(solver, O):
     _eq(u0, o.reset(B)[0], "reset plan")
     for a, b, w in zip(s.rollout(x, u0, u0[:, 0], curr_t=ct, rng=rng), o.rollout(x, u0, u0[:, 0], curr_t=ct, rng=rng), "Jgx"):
         _eq(a, b, f"trajectory mode {w}")
-    cfgp, sp, op = _pair(solver, O, "iris", "pos")
+    for a, b, w in zip(s.solve(x, u0, i0, curr_t=ct, rng=rng)[:3], o.solve(x, u0, i0, curr_t=ct, rng=rng)[:3], "uxi"):
+        _eq(a[..., :7] if w == "i" else a, b[..., :7] if w == "i" else b, f"trajectory-mode solve {w} {mode}")
+    cfgp, sp, op = _pair(solver, O, "iris", "pos", max_iter=12, **mode)
     xd = random_states(B, 4)
     for a, b, w in zip(sp.rollout(x, u0, u0[:, 0], xdes=xd, rng=rng), op.rollout(x, u0, u0[:, 0], xdes=xd, rng=rng), "Jgx"):
         _eq(a, b, f"set-point mode {w}")
+    xi = np.random.default_rng(5).standard_normal((B, 1, cfg.horizon, 6)).astype(np.float32)
+    for a, b, w in zip(sp.solve(x, u0, i0, xdes=xd, xi=xi)[:3], op.solve(x, u0, i0, xdes=xd, xi=xi)[:3], "uxi"):
+        _eq(a[..., :7] if w == "i" else a, b[..., :7] if w == "i" else b, f"set-point solve with explicit noise {w} {mode}")
 
 
 @pytest.mark.parametrize("vehicle,mode,P,iters", [("iris", "traj", 1, 200), ("iris", "pos", 1, 100), ("iris", "traj", 8, 40),
