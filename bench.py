@@ -321,8 +321,12 @@ def main():
     flops_launch = algorithmic_flops(info, H, P, F_STEP["iris"])
     achieved_tf = flops_launch / (kern_ms * 1e-3) / 1e12
     alg_bytes = B * (13 * 4 + (H + 1) * 13 * 4 + 2 * H * nu * 4 + (H + 1) * 13 * 4 + 2 * 32 + 16) + 2 * (1536 + 70) * 4
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and B == 4096 and args.max_iter == 200:
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     roofline = {"bound": "fp32", "achieved": achieved_tf, "peak": pk["fp32_tflops"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["fp32_tflops"], "traffic": None,
+                "frac": achieved_tf / pk["fp32_tflops"], "traffic": traffic,
                 "peak_source": f"148 SM x 128 lanes x 2 x {pk['sm_max_mhz']:.0f} MHz ({pk['source']} clock; MEASURED_PEAKS.json has no FP32-pipe figure)",
                 "kernel": kernel_name, "avg_launch_ms": kern_ms, "algorithmic_flop_per_launch": flops_launch,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kern_ms * 1e-3) / 1e9,
