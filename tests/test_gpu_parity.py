@@ -160,6 +160,36 @@ def test_three_kernels_agree(solver, O, vehicle, width):
         _eq(info[:, :7], infoo[:n, :7], f"telemetry {mode}"); _eq(tr, tro[:n], f"trace {mode}")
 
 
+@pytest.mark.parametrize("mode", [{}, {"group": True}, {"sequential_ls": True}])
+def test_nondefault_schedule_and_options(solver, O, mode):
+    """Horizon 12 with a short/long step grid, discount < 1, conservative step-size reset, maxls = 6 (two rounds
+    of the concurrent line search), no warm-start shift: every option of the YAML schema that the BASELINE
+    configs leave at its default still matches the oracle bit for bit on all three kernels."""
+    import os
+
+    from conftest import ROOT
+    from sde4mbrl_px4_b200 import config, model_io
+
+    cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
+    cfgd.update(horizon=12, num_short_dt=5, short_step_dt=0.04, long_step_dt=0.1, discount=0.97)
+    cfgd["apg_mpc"]["linesearch"].update(maxls=6, reset_option="conservative", init_stepsize=3e-3, decrease_factor=0.5)
+    cfgd["apg_mpc"].update(max_iter=30, max_no_improvement_iter=1)
+    cfg = config.build_config(cfgd, no_shift=True, **mode)
+    assert cfg.horizon == 12 and abs(cfg.dt[4] - 0.04) < 1e-7 and abs(cfg.dt[5] - 0.1) < 1e-7 and cfg.reset_option == 0
+    blob = model_io.synthetic_model("iris").to_blob()
+    s, o = solver.MPCSolver(cfg, blob), O.Oracle(cfg, blob, "f32")
+    B = 21
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=31)
+    u0, i0 = s.reset(B)
+    u0 = np.clip(u0 + 0.05 * np.random.default_rng(1).standard_normal(u0.shape), 1e-4, 1).astype(np.float32)
+    a = s.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+    b = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+    _eq(a[3], b[3], f"trace {mode}"); _eq(a[0], b[0], f"u* {mode}"); _eq(a[1], b[1], f"x_evol {mode}")
+    _eq(a[2][:, :7], b[2][:, :7], f"telemetry {mode}")
+    assert a[3][:, :, 3].max() > 4          # some iteration needed more than 4 trials
+    assert len(set(a[2][:, 2])) > 1         # early stops (no-improvement budget) at different iterations
+
+
 def test_early_stopping_with_yaml_tolerances(solver, O):
     """Default YAML tolerances (rtol 1e-6, atol 1e-8): per-problem iteration counts differ and still match."""
     cfg, s, o = _pair(solver, O, "iris", "pos")
