@@ -51,7 +51,7 @@ struct KParams {
     float2* mtape_g;     // global MLP tape scratch (W = 64), per resident warp
     // per-warp shared-memory layout (float offsets), computed on the host
     int ws_stride, o_xk, o_yk, o_g, o_xp, o_uprev, o_xref, o_xi, o_xtape, o_stape, o_mtape, o_bufA, o_bufB,
-        o_act3, o_lz, o_red, o_zb, o_lob;
+        o_act3, o_lz, o_red, o_zb, o_lob, o_g2;
     int gx_stride;       // group kernel: floats of per-warp exchange buffers (bufA | bufB | act3)
     int team_stride;     // per-team scratch (P > 1): floats
     // batch I/O (device pointers)
@@ -184,7 +184,7 @@ struct Warp {
     static constexpr int NIN = L::NIN, UPL = L::UPL;
     int lane;
     const float* ws;   // CTA weight image in shared memory
-    float *xk, *yk, *g, *xp, *uprev, *xref, *xi, *xtape, *stape, *bufA, *bufB, *act3, *lz, *red;
+    float *xk, *yk, *g, *g2, *xp, *uprev, *xref, *xi, *xtape, *stape, *bufA, *bufB, *act3, *lz, *red;
     float2* mtape;     // [H][2][W] (shared or global)
     // W == 32: forward rows in registers
     float2 w1[L::WREG ? UPL : 1][L::WREG ? NIN : 1];
@@ -798,7 +798,8 @@ struct Team {
     int warp_in_team;   // particle index
     int bar_id;         // named barrier (P > 1)
     float* scratch;     // team scratch in shared memory: [PP] costs
-    float* warp0_base;  // per-warp region of the team's first warp
+    float* warp0_base;  // per-warp region of the team's first warp (of this replica when LSW > 1)
+    float* team0_base;  // per-warp region of the first warp of the whole team (all replicas)
     int ws_stride;
     int ls_index;       // speculative line search: this warp evaluates trial `ls_index` (0 when LSW == 1)
     int ls_bar_id;      // named barrier of the LSW sibling warps
@@ -981,6 +982,180 @@ __device__ __forceinline__ void apg_solve(const KParams& P, Warp<NU, W>& c, cons
             tr[0] = fy; tr[1] = Jp; tr[2] = s; tr[3] = (float)n_ls; tr[4] = accept ? 1.f : 0.f; tr[5] = Jx; tr[6] = gsq; tr[7] = (float)k;
         }
         if (it >= P.max_iter || no_improve >= P.max_no_improve || converged || !(fy == fy)) break;
+    }
+    (void)rollout_fwd<NU, W, 2>(P, c, c.xk, x0);
+    __syncwarp();
+    inf.avg_linesearch = __fdiv_rn(sum_ls, (float)it);
+    inf.stepsize = s;
+    inf.num_steps = (float)it;
+    inf.grad_sqr = gsq;
+    inf.avg_stepsize = __fdiv_rn(sum_s, (float)it);
+    inf.init_cost = init_cost;
+    inf.opt_cost = (Jx == Jx) ? Jx : __int_as_float(0x7f800000);
+    inf.solve_time_us = 0.f;
+}
+
+// ---------------------------------------------------------------------------------
+// Latency-mode APG solve (P = 1): LSW line-search warps + SGW speculative-gradient warps run the same solve
+// as replicas.  Per iteration, while LS warp l evaluates trial l (step s*dec^l), speculation warp c already
+// computes value_and_grad at the NEXT extrapolation point for one possible outcome of the line search
+// (c < SGW-1: "trial c accepted"; c = SGW-1: "step rejected", where the next point is x_k itself).  When the
+// outcome is one of those, the next iteration starts with its gradient already known and the line search is
+// off the critical path; otherwise every warp computes the gradient as usual.  Candidates are built with the
+// same arithmetic as the real update, so the result is bit-identical to the sequential solve.
+// ---------------------------------------------------------------------------------
+template <int NU, int W, int LSW, int SGW>
+__device__ __forceinline__ void apg_solve_latency(const KParams& P, Warp<NU, W>& c, const Team<1>& tm, const float (&x0)[NX],
+                                                  float s, sdempc_info& inf, float* trace) {
+    constexpr int TW = LSW + SGW;
+    const int lane = c.lane;
+    const int n = P.H * NU;
+    const int l = tm.ls_index;              // 0..LSW-1: line-search warp; LSW..TW-1: speculation warp
+    const bool is_spec = (l >= LSW);
+    const int cand = l - LSW;               // speculation candidate of this warp (if is_spec)
+    float* const ls_slots = tm.scratch;            // [2][LSW][2]
+    float* const sg_slots = tm.scratch + 4 * LSW;  // [SGW]
+    auto team_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(tm.ls_bar_id), "r"(TW * 32) : "memory"); };
+    for (int i = lane; i < n; i += 32) c.yk[i] = c.xk[i];
+    __syncwarp();
+    float Jx = 0.f, Jp = 0.f, fy = 0.f, gsq = 0.f, sum_ls = 0.f, sum_s = 0.f, init_cost = 0.f;
+    int k = 1, no_improve = 0, it = 0, ls_round = 0;
+    bool boot = true;
+    for (;;) {
+        if (boot) {   // gradient at y_k computed by every replica (first iteration, or a speculation miss)
+            ++it;
+            fy = rollout_fwd<NU, W, 1>(P, c, c.yk, x0);
+            rollout_bwd<NU, W>(P, c, c.yk);
+            if (it == 1) { Jx = fy; init_cost = fy; }
+        }
+        {
+            float part = 0.f;
+            for (int i = lane; i < n; i += 32) { const float gi = c.g[i]; part = fma_(gi, gi, part); }
+            gsq = warp_butterfly(part);
+        }
+        if (P.reset_option == 1) { s = s * P.inc_f; s = s > P.max_step ? P.max_step : s; }
+        const float s0 = s;
+        const float beta = __fdiv_rn((float)k, (float)(k + 3));
+        // ---- speculation warps: value_and_grad at the candidate next point, into g2 ----
+        bool spec_valid = false;
+        if (SGW > 0 && is_spec) {
+            const bool rej = (cand == SGW - 1);
+            if (rej || cand <= P.maxls) {
+                float s_c = s0;
+                for (int q = 0; q < cand && !rej; ++q) s_c = s_c * P.dec_f;
+                for (int i = lane; i < n; i += 32) {
+                    const int ii = i % NU;
+                    float v;
+                    if (rej) v = c.xk[i];
+                    else {
+                        const float xv = clipf(fma_(-s_c, c.g[i], c.yk[i]), P.u_lo[ii], P.u_hi[ii]);
+                        v = clipf(fma_(beta, xv - c.xk[i], xv), P.u_lo[ii], P.u_hi[ii]);
+                    }
+                    c.xp[i] = v;
+                }
+                __syncwarp();
+                spec_valid = true;
+            }
+        }
+        // ---- line search in rounds of LSW concurrent trials (see apg_solve) ----
+        bool ok = false;
+        int n_ls = 0, jsel = 0, base = 0;
+        float s_base = s0;
+        float* slot = nullptr;
+        for (int round = 0;; ++round) {
+            const int j = base + l;
+            slot = ls_slots + 2 * LSW * (ls_round & 1);
+            ++ls_round;
+            float Jl = 0.f, dec = 0.f;
+            bool do_trial = !is_spec && j <= P.maxls;
+            if (do_trial) {
+                float s_l = s_base;
+                for (int q = 0; q < l; ++q) s_l = s_l * P.dec_f;
+                float part = 0.f;
+                for (int i = lane; i < n; i += 32) {
+                    const int ii = i % NU;
+                    const float gi = c.g[i], yi = c.yk[i];
+                    const float xv = clipf(fma_(-s_l, gi, yi), P.u_lo[ii], P.u_hi[ii]);
+                    c.xp[i] = xv;
+                    part = fma_(gi, xv - yi, part);
+                }
+                dec = warp_butterfly(part);
+                __syncwarp();
+            }
+            const bool do_grad = is_spec && spec_valid && round == 0;
+            if (do_grad) {   // speculative value_and_grad at c.xp -> c.g2
+                float* gsave = c.g;
+                c.g = c.g2;
+                const float fc = rollout_fwd<NU, W, 1>(P, c, c.xp, x0);
+                rollout_bwd<NU, W>(P, c, c.xp);
+                c.g = gsave;
+                if (lane == 0) sg_slots[cand] = fc;
+            }
+            if (do_trial) {
+                Jl = rollout_fwd<NU, W, 0>(P, c, c.xp, x0);
+                if (lane == 0) { slot[2 * l] = Jl; slot[2 * l + 1] = (Jl <= fma_(P.coef, dec, fy)) ? 1.f : 0.f; }
+            }
+            team_bar();
+            int q = 0;
+            for (; q < LSW && base + q <= P.maxls; ++q)
+                if (slot[2 * q + 1] != 0.f) { ok = true; break; }
+            if (ok) { jsel = base + q; break; }
+            if (base + LSW > P.maxls) { jsel = P.maxls; break; }   // every trial failed
+            for (int r = 0; r < LSW; ++r) s_base = s_base * P.dec_f;
+            base += LSW;
+        }
+        s = s0;
+        for (int q = 0; q < jsel; ++q) s = s * P.dec_f;
+        Jp = slot[2 * (jsel - base)];
+        n_ls = jsel + 1;
+        // adopt the selected trial point (same arithmetic as the warp that evaluated it)
+        for (int i = lane; i < n; i += 32) {
+            const int ii = i % NU;
+            c.xp[i] = clipf(fma_(-s, c.g[i], c.yk[i]), P.u_lo[ii], P.u_hi[ii]);
+        }
+        __syncwarp();
+        sum_ls = sum_ls + (float)n_ls;
+        sum_s = sum_s + s;
+        const bool accept = ok && (Jp <= Jx);
+        bool converged = false;
+        if (accept) {
+            for (int i = lane; i < n; i += 32) {
+                const int ii = i % NU;
+                const float xv = c.xp[i];
+                c.yk[i] = clipf(fma_(beta, xv - c.xk[i], xv), P.u_lo[ii], P.u_hi[ii]);
+                c.xk[i] = xv;
+            }
+            const float Jprev = Jx;
+            Jx = Jp; ++k; no_improve = 0;
+            const float tol = P.atol + P.rtol * fabsf(Jprev);
+            converged = (fabsf(Jprev - Jx) <= tol) || (Jx <= P.atol);
+        } else {
+            for (int i = lane; i < n; i += 32) c.yk[i] = c.xk[i];
+            k = 1; ++no_improve;
+        }
+        __syncwarp();
+        if (trace != nullptr && l == 0 && lane == 0) {
+            float* tr = trace + (size_t)(it - 1) * SDEMPC_TRACE_W;
+            tr[0] = fy; tr[1] = Jp; tr[2] = s; tr[3] = (float)n_ls; tr[4] = accept ? 1.f : 0.f; tr[5] = Jx; tr[6] = gsq; tr[7] = (float)k;
+        }
+        if (it >= P.max_iter || no_improve >= P.max_no_improve || converged || !(fy == fy)) break;
+        // ---- did a speculation warp already compute the gradient at the new y_k? ----
+        int hit = -1;
+        if (SGW > 0) {
+            if (!accept) hit = SGW - 1;
+            else if (jsel < SGW - 1) hit = jsel;
+        }
+        if (hit >= 0) {
+            ++it;
+            fy = sg_slots[hit];
+            const float* src = tm.team0_base + (size_t)(LSW + hit) * tm.ws_stride + P.o_g2;
+            for (int i = lane; i < n; i += 32) c.g[i] = src[i];
+            __syncwarp();
+            boot = false;
+        } else {
+            boot = true;
+        }
+        if (SGW > 0) team_bar();   // g2 / slots may be overwritten by the next pass
     }
     (void)rollout_fwd<NU, W, 2>(P, c, c.xk, x0);
     __syncwarp();

@@ -101,8 +101,8 @@ __device__ __forceinline__ void write_x_evol(const KParams& P, const Team<PP>& t
     tm.sync();   // tapes may be overwritten by the next problem
 }
 
-template <int NU, int W, int PP, int G, int MODE, int LSW = 1>
-__global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
+template <int NU, int W, int PP, int G, int MODE, int LSW = 1, int SGW = 0>
+__global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
     using L = Layout<NU, W>;
     extern __shared__ __align__(128) float smem[];
     float* ws = smem;
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
     float* warp_base = team_base + G * P.team_stride;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int WPT = PP * LSW;   // warps per team
+    constexpr int WPT = PP * (LSW + SGW);   // warps per team
     const int team = warp / WPT, wit = (warp % WPT) % PP, ls = (warp % WPT) / PP;
 
     stage_weights<L::SMEM_FLOATS * 4>(ws, P.wimg, bar);
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
     c.lane = lane;
     c.ws = ws;
     float* wb = warp_base + (size_t)warp * P.ws_stride;
-    c.xk = wb + P.o_xk; c.yk = wb + P.o_yk; c.g = wb + P.o_g; c.xp = wb + P.o_xp; c.uprev = wb + P.o_uprev;
+    c.xk = wb + P.o_xk; c.yk = wb + P.o_yk; c.g = wb + P.o_g; c.g2 = wb + P.o_g2; c.xp = wb + P.o_xp; c.uprev = wb + P.o_uprev;
     c.xref = wb + P.o_xref; c.xi = wb + P.o_xi; c.xtape = wb + P.o_xtape; c.stape = wb + P.o_stape;
     c.bufA = wb + P.o_bufA; c.bufB = wb + P.o_bufB; c.act3 = wb + P.o_act3; c.lz = wb + P.o_lz; c.red = wb + P.o_red;
     if (P.mtape_g != nullptr)
@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
     tm.bar_id = 1 + team;
     tm.scratch = team_base + team * P.team_stride;
     tm.warp0_base = warp_base + (size_t)(team * WPT + ls * PP) * P.ws_stride;
+    tm.team0_base = warp_base + (size_t)(team * WPT) * P.ws_stride;
     tm.ws_stride = P.ws_stride;
     tm.ls_index = ls;
     tm.ls_bar_id = 1 + team;
@@ -183,7 +184,9 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
             float s = P.info[b].stepsize;
             s = s > 0.f ? s : P.init_step;
             sdempc_info inf;
-            apg_solve<NU, W, PP, LSW>(P, c, tm, x0, s, inf, P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
+            float* trp = P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr;
+            if constexpr (LSW > 1) apg_solve_latency<NU, W, LSW, SGW>(P, c, tm, x0, s, inf, trp);
+            else apg_solve<NU, W, PP, 1>(P, c, tm, x0, s, inf, trp);
             float* pout = P.u_plan_out + (size_t)b * n;
             if (wit == 0 && ls == 0) {
                 for (int i = lane; i < n; i += 32) pout[i] = c.xk[i];
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(G* PP* LSW * 32, 1) mpc_kernel(const __grid_co
                     __syncwarp();
                 }
                 sdempc_info inf;
-                apg_solve<NU, W, PP, LSW>(P, c, tm, x0, s, inf, nullptr);
+                if constexpr (LSW > 1) apg_solve_latency<NU, W, LSW, SGW>(P, c, tm, x0, s, inf, nullptr);
+                else apg_solve<NU, W, PP, 1>(P, c, tm, x0, s, inf, nullptr);
                 s = inf.stepsize;
                 sc = sc + inf.opt_cost;
                 sn = sn + inf.num_steps;
@@ -419,7 +423,8 @@ static int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr int GROUP_GP = 4, GROUP_GW = 8;   // problems per warp / warps per CTA of the throughput kernel
-constexpr int SPEC_LSW = 4;   // sibling warps of the speculative line search: one per SM sub-partition
+constexpr int SPEC_LSW = 4;   // line-search warps of the latency kernel: one per SM sub-partition
+constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0/1/2 accepted, step rejected)
 
 struct KernelChoice {
     void (*solve)(KParams);
@@ -445,8 +450,8 @@ static KernelChoice make_choice() {
     k.solve_group = nullptr;
     if constexpr (PP == 1 && W == 32) k.solve_group = mpc_group_kernel<NU, W, GROUP_GP, GROUP_GW>;
     if constexpr (PP == 1) {
-        k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW>;
-        k.closed_spec = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW>;
+        k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW, SPEC_SGW>;
+        k.closed_spec = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW, SPEC_SGW>;
     }
     k.nu = NU; k.W = W; k.P = PP; k.G = G;
     k.wimg_floats = L::TOTAL; k.wsmem_floats = L::SMEM_FLOATS; k.wreg = L::WREG;
@@ -565,7 +570,7 @@ static void build_kparams(sdempc_handle* h) {
     // per-warp shared layout
     const int H = c.horizon, NU = c.nu, W = m.width, n = align4(H * NU);
     int o = 0;
-    k.o_xk = o; o += n; k.o_yk = o; o += n; k.o_g = o; o += n; k.o_xp = o; o += n;
+    k.o_xk = o; o += n; k.o_yk = o; o += n; k.o_g = o; o += n; k.o_xp = o; o += n; k.o_g2 = o; o += n;
     k.o_uprev = o; o += 8;
     k.o_xref = o; o += (H + 1) * 16;
     k.o_xi = o; o += H * 8;
@@ -583,7 +588,7 @@ static void build_kparams(sdempc_handle* h) {
     const KernelChoice& kc = h->kc;
     const size_t floats = (size_t)kc.wsmem_floats + 4 + (size_t)kc.G * k.team_stride + (size_t)kc.G * kc.P * k.ws_stride;
     h->smem_bytes = floats * 4;
-    h->smem_bytes_spec = ((size_t)kc.wsmem_floats + 4 + (size_t)k.team_stride + (size_t)SPEC_LSW * k.ws_stride) * 4;
+    h->smem_bytes_spec = ((size_t)kc.wsmem_floats + 4 + (size_t)k.team_stride + (size_t)(SPEC_LSW + SPEC_SGW) * k.ws_stride) * 4;
     // group kernel: per-problem regions hold only problem data; exchange buffers are per warp; the
     // activation tape lives in global memory (L2 resident)
     KParams& g = h->kp_group;
@@ -677,7 +682,7 @@ static int ensure_mtape_group(sdempc_handle* h, int grid) {
 
 static int ensure_mtape(sdempc_handle* h, int grid) {
     if (h->mh.width == 32) return 0;
-    const size_t warps = (size_t)grid * std::max(h->kc.G * h->kc.P, SPEC_LSW);
+    const size_t warps = (size_t)grid * std::max(h->kc.G * h->kc.P, SPEC_LSW + SPEC_SGW);
     if (warps <= h->mtape_warps) return 0;
     if (h->d_mtape) cudaFree(h->d_mtape);
     h->d_mtape = nullptr;
@@ -796,7 +801,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
-    const int threads = spec ? SPEC_LSW * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    const int threads = spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     const size_t smem = spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
     void* args[] = {const_cast<KParams*>(&k)};
     CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, smem, h->stream));
@@ -1120,7 +1125,7 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
-    out[0] = h->staged_spec ? SPEC_LSW * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    out[0] = h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
     out[2] = h->staged_spec ? 1 : h->staged_group ? GROUP_GW * GROUP_GP : h->kc.G;
     out[3] = h->regs;
