@@ -58,6 +58,7 @@ extern "C" {
 #define SDEMPC_F_SPECULATIVE_LS 4u /* force latency mode: all line-search trials evaluated concurrently on sibling warps */
 #define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
 #define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
+#define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a 2-CTA cluster */
 /* Default kernel choice: latency kernel when B <= number of SMs, throughput kernel above (P = 1, width 32),
  * one warp per problem otherwise.  All three produce bit-identical results. */
 

@@ -22,6 +22,7 @@ F_NO_SHIFT = 2
 F_SPECULATIVE_LS = 4
 F_SEQUENTIAL_LS = 8
 F_GROUP = 16
+F_NO_CLUSTER = 32
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 

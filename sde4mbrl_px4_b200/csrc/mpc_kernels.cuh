@@ -800,6 +800,7 @@ struct Team {
     float* scratch;     // team scratch in shared memory: [PP] costs
     float* warp0_base;  // per-warp region of the team's first warp (of this replica when LSW > 1)
     float* team0_base;  // per-warp region of the first warp of the whole team (all replicas)
+    float* spec0_base;  // per-warp region of the team's first speculation warp (possibly in the sibling CTA)
     int ws_stride;
     int ls_index;       // speculative line search: this warp evaluates trial `ls_index` (0 when LSW == 1)
     int ls_bar_id;      // named barrier of the LSW sibling warps
@@ -1004,7 +1005,10 @@ __device__ __forceinline__ void apg_solve(const KParams& P, Warp<NU, W>& c, cons
 // off the critical path; otherwise every warp computes the gradient as usual.  Candidates are built with the
 // same arithmetic as the real update, so the result is bit-identical to the sequential solve.
 // ---------------------------------------------------------------------------------
-template <int NU, int W, int LSW, int SGW>
+// CL = 1: the two halves of the team are the two CTAs of a thread-block cluster (line-search warps on one SM,
+// speculation warps on the neighbouring SM, so that neither slows the other down); slots and gradients are
+// exchanged through distributed shared memory and the team barrier is the cluster barrier.
+template <int NU, int W, int LSW, int SGW, int CL>
 __device__ __forceinline__ void apg_solve_latency(const KParams& P, Warp<NU, W>& c, const Team<1>& tm, const float (&x0)[NX],
                                                   float s, sdempc_info& inf, float* trace) {
     constexpr int TW = LSW + SGW;
@@ -1015,7 +1019,10 @@ __device__ __forceinline__ void apg_solve_latency(const KParams& P, Warp<NU, W>&
     const int cand = l - LSW;               // speculation candidate of this warp (if is_spec)
     float* const ls_slots = tm.scratch;            // [2][LSW][2]
     float* const sg_slots = tm.scratch + 4 * LSW;  // [SGW]
-    auto team_bar = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(tm.ls_bar_id), "r"(TW * 32) : "memory"); };
+    auto team_bar = [&]() {
+        if constexpr (CL) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        else asm volatile("bar.sync %0, %1;" ::"r"(tm.ls_bar_id), "r"(TW * 32) : "memory");
+    };
     for (int i = lane; i < n; i += 32) c.yk[i] = c.xk[i];
     __syncwarp();
     float Jx = 0.f, Jp = 0.f, fy = 0.f, gsq = 0.f, sum_ls = 0.f, sum_s = 0.f, init_cost = 0.f;
@@ -1148,7 +1155,7 @@ __device__ __forceinline__ void apg_solve_latency(const KParams& P, Warp<NU, W>&
         if (hit >= 0) {
             ++it;
             fy = sg_slots[hit];
-            const float* src = tm.team0_base + (size_t)(LSW + hit) * tm.ws_stride + P.o_g2;
+            const float* src = tm.spec0_base + (size_t)hit * tm.ws_stride + P.o_g2;
             for (int i = lane; i < n; i += 32) c.g[i] = src[i];
             __syncwarp();
             boot = false;
@@ -1157,6 +1164,7 @@ __device__ __forceinline__ void apg_solve_latency(const KParams& P, Warp<NU, W>&
         }
         if (SGW > 0) team_bar();   // g2 / slots may be overwritten by the next pass
     }
+    if (SGW > 0) team_bar();       // nobody still reads this solve's slots when the next one starts writing
     (void)rollout_fwd<NU, W, 2>(P, c, c.xk, x0);
     __syncwarp();
     inf.avg_linesearch = __fdiv_rn(sum_ls, (float)it);

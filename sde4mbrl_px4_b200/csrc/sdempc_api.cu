@@ -5,6 +5,7 @@
 //        -shared -Xcompiler -fPIC -cudart static sdempc_api.cu -o ../libsdempc.so
 // -fmad=false is REQUIRED: every fused multiply-add of SPEC-ARITH is written
 // explicitly (__fmaf_rn / __ffma2_rn); nothing else may be contracted.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -101,8 +102,11 @@ __device__ __forceinline__ void write_x_evol(const KParams& P, const Team<PP>& t
     tm.sync();   // tapes may be overwritten by the next problem
 }
 
-template <int NU, int W, int PP, int G, int MODE, int LSW = 1, int SGW = 0>
-__global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
+// CL = 1 (latency kernel on a 2-CTA cluster): CTA rank 0 holds the LSW line-search warps, rank 1 the SGW
+// speculation warps of ONE problem; launched with cluster dimension 2.
+template <int NU, int W, int PP, int G, int MODE, int LSW = 1, int SGW = 0, int CL = 0>
+__global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) mpc_kernel(const __grid_constant__ KParams P) {
+    static_assert(!CL || (G == 1 && PP == 1 && LSW == SGW), "cluster mode: one problem, equal halves");
     using L = Layout<NU, W>;
     extern __shared__ __align__(128) float smem[];
     float* ws = smem;
@@ -111,8 +115,10 @@ __global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __
     float* warp_base = team_base + G * P.team_stride;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int WPT = PP * (LSW + SGW);   // warps per team
-    const int team = warp / WPT, wit = (warp % WPT) % PP, ls = (warp % WPT) / PP;
+    constexpr int WPT = CL ? LSW : PP * (LSW + SGW);   // warps per team (per CTA in cluster mode)
+    unsigned crank = 0;
+    if constexpr (CL) crank = cooperative_groups::this_cluster().block_rank();
+    const int team = warp / WPT, wit = (warp % WPT) % PP, ls = (warp % WPT) / PP + (CL ? (int)crank * LSW : 0);
 
     stage_weights<L::SMEM_FLOATS * 4>(ws, P.wimg, bar);
 
@@ -135,6 +141,12 @@ __global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __
     tm.scratch = team_base + team * P.team_stride;
     tm.warp0_base = warp_base + (size_t)(team * WPT + ls * PP) * P.ws_stride;
     tm.team0_base = warp_base + (size_t)(team * WPT) * P.ws_stride;
+    tm.spec0_base = tm.team0_base + (size_t)LSW * P.ws_stride;
+    if constexpr (CL) {   // slots live in CTA 0, speculation gradients in CTA 1: distributed shared memory
+        auto cluster = cooperative_groups::this_cluster();
+        tm.scratch = cluster.map_shared_rank(team_base, 0);
+        tm.spec0_base = cluster.map_shared_rank(warp_base, 1);
+    }
     tm.ws_stride = P.ws_stride;
     tm.ls_index = ls;
     tm.ls_bar_id = 1 + team;
@@ -144,7 +156,9 @@ __global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __
     const int n = P.H * NU;
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
 
-    for (int b = blockIdx.x * G + team; b < P.B; b += gridDim.x * G) {
+    const int b_first = CL ? (int)(blockIdx.x / 2) : (int)(blockIdx.x * G + team);
+    const int b_step = CL ? (int)(gridDim.x / 2) : (int)(gridDim.x * G);
+    for (int b = b_first; b < P.B; b += b_step) {
         // ---- state ----
         float x0[NX];
         {
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __
             s = s > 0.f ? s : P.init_step;
             sdempc_info inf;
             float* trp = P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr;
-            if constexpr (LSW > 1) apg_solve_latency<NU, W, LSW, SGW>(P, c, tm, x0, s, inf, trp);
+            if constexpr (LSW > 1) apg_solve_latency<NU, W, LSW, SGW, CL>(P, c, tm, x0, s, inf, trp);
             else apg_solve<NU, W, PP, 1>(P, c, tm, x0, s, inf, trp);
             float* pout = P.u_plan_out + (size_t)b * n;
             if (wit == 0 && ls == 0) {
@@ -248,7 +262,7 @@ __global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __
                     __syncwarp();
                 }
                 sdempc_info inf;
-                if constexpr (LSW > 1) apg_solve_latency<NU, W, LSW, SGW>(P, c, tm, x0, s, inf, nullptr);
+                if constexpr (LSW > 1) apg_solve_latency<NU, W, LSW, SGW, CL>(P, c, tm, x0, s, inf, nullptr);
                 else apg_solve<NU, W, PP, 1>(P, c, tm, x0, s, inf, nullptr);
                 s = inf.stepsize;
                 sc = sc + inf.opt_cost;
@@ -292,6 +306,7 @@ __global__ void __launch_bounds__(G* PP*(LSW + SGW) * 32, 1) mpc_kernel(const __
             tm.sync();
         }
     }
+    if constexpr (CL) cooperative_groups::this_cluster().sync();   // keep shared memory alive for the sibling CTA
 }
 
 // Throughput kernel: GW warps per CTA, each warp owns GP problems (mpc_group.cuh).  P = 1.
@@ -432,6 +447,8 @@ struct KernelChoice {
     void (*closed)(KParams);
     void (*solve_spec)(KParams);   // latency mode: one problem per CTA, SPEC_LSW warps (P == 1 only)
     void (*closed_spec)(KParams);
+    void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
+    void (*closed_cl)(KParams);
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x GROUP_GP problems per CTA (P == 1, W == 32)
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
@@ -447,11 +464,14 @@ static KernelChoice make_choice() {
     k.closed = mpc_kernel<NU, W, PP, G, MODE_CLOSED_LOOP>;
     k.solve_spec = nullptr;
     k.closed_spec = nullptr;
+    k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     if constexpr (PP == 1 && W == 32) k.solve_group = mpc_group_kernel<NU, W, GROUP_GP, GROUP_GW>;
     if constexpr (PP == 1) {
         k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW, SPEC_SGW>;
         k.closed_spec = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW, SPEC_SGW>;
+        k.solve_cl = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW, SPEC_SGW, 1>;
+        k.closed_cl = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW, SPEC_SGW, 1>;
     }
     k.nu = NU; k.W = W; k.P = PP; k.G = G;
     k.wimg_floats = L::TOTAL; k.wsmem_floats = L::SMEM_FLOATS; k.wreg = L::WREG;
@@ -480,7 +500,7 @@ struct sdempc_handle {
     KParams kp;                       // template (config + model + layout)
     KParams kp_group;                 // same with the per-problem layout of the group kernel
     size_t smem_bytes_group = 0;
-    size_t smem_bytes = 0, smem_bytes_spec = 0;
+    size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
     bool dev_ready = false;
     cudaStream_t stream = nullptr;
@@ -502,7 +522,7 @@ struct sdempc_handle {
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false;
     float last_ms = 0.f;
 };
 
@@ -589,6 +609,7 @@ static void build_kparams(sdempc_handle* h) {
     const size_t floats = (size_t)kc.wsmem_floats + 4 + (size_t)kc.G * k.team_stride + (size_t)kc.G * kc.P * k.ws_stride;
     h->smem_bytes = floats * 4;
     h->smem_bytes_spec = ((size_t)kc.wsmem_floats + 4 + (size_t)k.team_stride + (size_t)(SPEC_LSW + SPEC_SGW) * k.ws_stride) * 4;
+    h->smem_bytes_cl = ((size_t)kc.wsmem_floats + 4 + (size_t)k.team_stride + (size_t)SPEC_LSW * k.ws_stride) * 4;
     // group kernel: per-problem regions hold only problem data; exchange buffers are per warp; the
     // activation tape lives in global memory (L2 resident)
     KParams& g = h->kp_group;
@@ -642,6 +663,10 @@ static int ensure_device(sdempc_handle* h) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.closed_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_spec));
     }
+    if (h->kc.solve_cl) {
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.closed_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl));
+    }
     if (h->kc.solve_group) {
         if (h->smem_bytes_group > (size_t)prop.sharedMemPerBlockOptin) h->kc.solve_group = nullptr;   // does not fit: use one warp per problem
         else CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_group));
@@ -663,6 +688,11 @@ static bool use_spec(const sdempc_handle* h, int B) {
     if (h->kc.solve_spec == nullptr || h->cfg.maxls < 1 || (h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS)) return false;
     if (h->cfg.flags & SDEMPC_F_SPECULATIVE_LS) return true;
     return !(h->cfg.flags & SDEMPC_F_GROUP) && B <= h->sm_count;
+}
+
+// cluster variant of the latency kernel: two SMs per problem
+static bool use_cluster(const sdempc_handle* h, int B) {
+    return use_spec(h, B) && h->kc.solve_cl != nullptr && 2 * B <= h->sm_count && !(h->cfg.flags & SDEMPC_F_NO_CLUSTER);
 }
 
 static bool use_group(const sdempc_handle* h, int B) {
@@ -762,7 +792,8 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
     const bool spec = use_spec(h, B), group = use_group(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
-    const int grid = spec ? std::min(B, h->sm_count)
+    const bool cl = use_cluster(h, B);
+    const int grid = cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
     if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
     else if ((rc = ensure_mtape(h, grid))) return rc;
@@ -794,11 +825,26 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
-    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group;
+    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl;
     return 0;
 }
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
+    if (fn != nullptr && (fn == h->kc.solve_cl || fn == h->kc.closed_cl)) {   // 2-CTA cluster per problem
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(SPEC_LSW * 32);
+        cfg.dynamicSmemBytes = h->smem_bytes_cl;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, k));
+        h->launches += 1;
+        return 0;
+    }
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
     const int threads = spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
@@ -969,7 +1015,7 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     for (int i = 0; i < n; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
+        int rc = launch(h, h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -1010,7 +1056,7 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     int rc = stage_solve(h, a);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
+    if ((rc = launch(h, h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
     float t = 0.f;
@@ -1089,8 +1135,8 @@ int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const flo
     const size_t xh = x_hist ? a16((size_t)R * (ticks + 1) * NX * 4) : 0, uh = u_hist ? a16((size_t)R * ticks * NU * 4) : 0;
     const size_t out_bytes = a16((size_t)R * 16) + xh + uh + 64;
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
-    const bool spec = use_spec(h, R);
-    const int grid = spec ? std::min(R, h->sm_count) : grid_for(h, R);
+    const bool spec = use_spec(h, R), cl = use_cluster(h, R);
+    const int grid = cl ? 2 * R : spec ? std::min(R, h->sm_count) : grid_for(h, R);
     if ((rc = ensure_mtape(h, grid))) return rc;
     KParams k = h->kp;
     Packer pk{h->h_in, h->d_in};
@@ -1106,7 +1152,7 @@ int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const flo
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
     h->staged_ok = false;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, spec ? h->kc.closed_spec : h->kc.closed, k, grid))) return rc;
+    if ((rc = launch(h, cl ? h->kc.closed_cl : spec ? h->kc.closed_spec : h->kc.closed, k, grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     h->last_grid = grid;
     CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, po.off, cudaMemcpyDeviceToHost, h->stream));
@@ -1125,7 +1171,7 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
-    out[0] = h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    out[0] = h->staged_cl ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
     out[2] = h->staged_spec ? 1 : h->staged_group ? GROUP_GW * GROUP_GP : h->kc.G;
     out[3] = h->regs;

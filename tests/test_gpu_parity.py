@@ -145,8 +145,9 @@ def test_three_kernels_agree(solver, O, vehicle, width):
     i0[::3, 1] = 3e-6                     # mixed carried step sizes
     uo, xeo, infoo, tro = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
     assert len(set(infoo[:, 2])) > 1 or True
-    modes = [(dict(speculative_ls=True), B, 255), (dict(sequential_ls=True), B, 256), (dict(), 9, 255),
-             (dict(), B, 256)]
+    # (flags, batch, expected threads per CTA; 255 = 8-warp latency kernel, 128 = 2-CTA cluster latency kernel)
+    modes = [(dict(speculative_ls=True), B, 255), (dict(sequential_ls=True), B, 256), (dict(), 9, 128),
+             (dict(no_cluster=True), 9, 255), (dict(), B, 256)]
     if w32:
         modes.append((dict(group=True), 7, 256))
     for mode, n, threads in modes:
@@ -154,8 +155,8 @@ def test_three_kernels_agree(solver, O, vehicle, width):
         u, xe, info, tr = s.solve(pr["x"][:n], u0[:n], i0[:n], xref_win=pr["xref_win"][:n], rng=pr["rng"][:n], want_trace=True)
         ki = s.kernel_info()
         assert ki["threads_per_cta"] == (256 if threads == 255 else threads), (mode, ki)
-        if threads == 255:
-            assert ki["problems_per_cta"] == 1, ki       # the latency kernel (4 line-search + 4 speculation warps)
+        if threads in (255, 128):
+            assert ki["problems_per_cta"] == 1, ki       # a latency kernel (4 line-search + 4 speculation warps)
         if vehicle == "iris" and (mode == dict(group=True) or (mode == dict() and n == B)):
             assert ki["problems_per_cta"] == 32, ki      # the throughput kernel was used
         _eq(u, uo[:n], f"u* {mode}"); _eq(xe, xeo[:n], f"x_evol {mode}")
