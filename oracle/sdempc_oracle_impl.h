@@ -62,6 +62,7 @@ typedef struct {
     REAL inv_m, gravity, kT, kT2, J[3], Jinv[3], Jd[3], mixer[3][SDEMPC_MAX_NU], sig0[6];
     /* [net 0 = drift, 1 = diffusion] */
     const float *W1[2], *b1[2], *W2[2], *b2[2], *W3[2], *b3[2];
+    float *W1T[2], *W2T[2];   /* transposed copies [in][out] for the vectorised forward layers */
 } CAT(omodel_, SUFFIX);
 #define OMODEL CAT(omodel_, SUFFIX)
 
@@ -93,6 +94,12 @@ static int FN(parse_model)(const void* blob, size_t nbytes, OMODEL* m) {
         m->b2[n] = p; p += W;
         m->W3[n] = p; p += 6 * (size_t)W;
         m->b3[n] = p; p += 6;
+        m->W1T[n] = (float*)malloc(sizeof(float) * (size_t)W * n_in);
+        m->W2T[n] = (float*)malloc(sizeof(float) * (size_t)W * W);
+        for (int j = 0; j < W; ++j) {
+            for (int k = 0; k < n_in; ++k) m->W1T[n][(size_t)k * W + j] = m->W1[n][(size_t)j * n_in + k];
+            for (int k = 0; k < W; ++k) m->W2T[n][(size_t)k * W + j] = m->W2[n][(size_t)j * W + k];
+        }
     }
     return 0;
 }
@@ -185,13 +192,29 @@ typedef struct {
 } CAT(otape_, SUFFIX);
 #define OTAPE CAT(otape_, SUFFIX)
 
+/* The layer loops run over the OUTPUT index in the inner loop (contiguous, auto-vectorised by gcc) while each
+ * output keeps the SPEC-ARITH accumulation order of dot4: partial sum (k mod 4), bias in partial 0, combined
+ * as (a0+a1)+(a2+a3).  Forward layers 1-2 use the transposed copies W1T[k][j], W2T[k][j] made at create(). */
 static void FN(mlp_fwd)(const OMODEL* m, OTAPE* tp) {
     const int W = m->width, n_in = m->n_in;
+    REAL acc[4][MAXW];
     for (int n = 0; n < 2; ++n) {
-        for (int j = 0; j < W; ++j)
-            tp->h1[n][j] = M_TANH(FN(dot4)(n_in, m->W1[n] + (size_t)j * n_in, 1, tp->z, (REAL)m->b1[n][j]));
-        for (int j = 0; j < W; ++j)
-            tp->h2[n][j] = M_TANH(FN(dot4)(W, m->W2[n] + (size_t)j * W, 1, tp->h1[n], (REAL)m->b2[n][j]));
+        for (int j = 0; j < W; ++j) { acc[0][j] = (REAL)m->b1[n][j]; acc[1][j] = 0; acc[2][j] = 0; acc[3][j] = 0; }
+        for (int k = 0; k < n_in; ++k) {
+            const float* w = m->W1T[n] + (size_t)k * W;
+            REAL* a = acc[k & 3];
+            const REAL zk = tp->z[k];
+            for (int j = 0; j < W; ++j) a[j] = FMA((REAL)w[j], zk, a[j]);
+        }
+        for (int j = 0; j < W; ++j) tp->h1[n][j] = M_TANH((acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]));
+        for (int j = 0; j < W; ++j) { acc[0][j] = (REAL)m->b2[n][j]; acc[1][j] = 0; acc[2][j] = 0; acc[3][j] = 0; }
+        for (int k = 0; k < W; ++k) {
+            const float* w = m->W2T[n] + (size_t)k * W;
+            REAL* a = acc[k & 3];
+            const REAL hk = tp->h1[n][k];
+            for (int j = 0; j < W; ++j) a[j] = FMA((REAL)w[j], hk, a[j]);
+        }
+        for (int j = 0; j < W; ++j) tp->h2[n][j] = M_TANH((acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j]));
         for (int o = 0; o < 6; ++o)
             tp->out[n][o] = FN(dot4)(W, m->W3[n] + (size_t)o * W, 1, tp->h2[n], (REAL)m->b3[n][o]);
     }
@@ -200,19 +223,36 @@ static void FN(mlp_fwd)(const OMODEL* m, OTAPE* tp) {
 /* lz[n_in] = J_drift^T lout[0] + J_diff^T lout[1] */
 static void FN(mlp_bwd)(const OMODEL* m, const OTAPE* tp, REAL lout[2][6], REAL* lz) {
     const int W = m->width, n_in = m->n_in;
-    REAL d2[MAXW], d1[2][MAXW];
+    REAL acc[4][MAXW], d2[MAXW], d1[MAXW], lzn[2][6 + SDEMPC_MAX_NU];
     for (int n = 0; n < 2; ++n) {
+        for (int c4 = 0; c4 < 4; ++c4) for (int j = 0; j < W; ++j) acc[c4][j] = 0;
+        for (int o = 0; o < 6; ++o) {
+            const float* w = m->W3[n] + (size_t)o * W;
+            REAL* a = acc[o & 3];
+            const REAL lo = lout[n][o];
+            for (int j = 0; j < W; ++j) a[j] = FMA((REAL)w[j], lo, a[j]);
+        }
+        for (int j = 0; j < W; ++j)
+            d2[j] = ((acc[0][j] + acc[1][j]) + (acc[2][j] + acc[3][j])) * FMA(-tp->h2[n][j], tp->h2[n][j], (REAL)1);
+        for (int c4 = 0; c4 < 4; ++c4) for (int k = 0; k < W; ++k) acc[c4][k] = 0;
         for (int j = 0; j < W; ++j) {
-            REAL a = FN(dot4)(6, m->W3[n] + j, W, lout[n], (REAL)0);
-            d2[j] = a * FMA(-tp->h2[n][j], tp->h2[n][j], (REAL)1);
+            const float* w = m->W2[n] + (size_t)j * W;
+            REAL* a = acc[j & 3];
+            const REAL dj = d2[j];
+            for (int k = 0; k < W; ++k) a[k] = FMA((REAL)w[k], dj, a[k]);
         }
-        for (int k = 0; k < W; ++k) {
-            REAL a = FN(dot4)(W, m->W2[n] + k, W, d2, (REAL)0);
-            d1[n][k] = a * FMA(-tp->h1[n][k], tp->h1[n][k], (REAL)1);
+        for (int k = 0; k < W; ++k)
+            d1[k] = ((acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k])) * FMA(-tp->h1[n][k], tp->h1[n][k], (REAL)1);
+        for (int c4 = 0; c4 < 4; ++c4) for (int i = 0; i < n_in; ++i) acc[c4][i] = 0;
+        for (int j = 0; j < W; ++j) {
+            const float* w = m->W1[n] + (size_t)j * n_in;
+            REAL* a = acc[j & 3];
+            const REAL dj = d1[j];
+            for (int i = 0; i < n_in; ++i) a[i] = FMA((REAL)w[i], dj, a[i]);
         }
+        for (int i = 0; i < n_in; ++i) lzn[n][i] = (acc[0][i] + acc[1][i]) + (acc[2][i] + acc[3][i]);
     }
-    for (int i = 0; i < n_in; ++i)
-        lz[i] = FN(dot4)(W, m->W1[0] + i, n_in, d1[0], (REAL)0) + FN(dot4)(W, m->W1[1] + i, n_in, d1[1], (REAL)0);
+    for (int i = 0; i < n_in; ++i) lz[i] = lzn[0][i] + lzn[1][i];
 }
 
 /* ---- rigid body helpers ------------------------------------------------------ */
@@ -656,6 +696,7 @@ int FN(create)(const sdempc_config* cfg, const void* blob, size_t nbytes, void**
 void FN(destroy)(void* hv) {
     OHANDLE* h = (OHANDLE*)hv;
     if (!h) return;
+    for (int n = 0; n < 2; ++n) { free(h->model.W1T[n]); free(h->model.W2T[n]); }
     free(h->blob); free(h->traj_ext); free(h->traj_int); free(h);
 }
 

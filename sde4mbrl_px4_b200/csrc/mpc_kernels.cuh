@@ -854,23 +854,18 @@ __device__ __forceinline__ void team_mean_grad(const KParams& P, const Team<PP>&
 // x0 the internal-frame state; s the carried step size.  On exit c.xk = u*, the
 // state tape holds this warp's particle trajectory at u*, and `inf` the telemetry.
 // ---------------------------------------------------------------------------------
-//
-// LSW > 1 (latency mode, P == 1): LSW sibling warps run the identical solve in lock step and differ only in
-// the line search, where warp l evaluates trial l (step s*dec^l) concurrently; the first trial that passes
-// the Armijo test is taken, which is exactly what the sequential search (LSW == 1) selects, so both modes
-// produce bit-identical results.  The only exchange is one (J, ok) pair per warp per iteration.
+// (The latency variant with concurrent line-search trials and speculative gradients is apg_solve_latency.)
 template <int NU, int W, int PP, int LSW>
 __device__ __forceinline__ void apg_solve(const KParams& P, Warp<NU, W>& c, const Team<PP>& tm, const float (&x0)[NX],
                                           float s, sdempc_info& inf, float* trace) {
-    static_assert(LSW == 1 || PP == 1, "speculative line search is implemented for one particle");
+    static_assert(LSW == 1, "the latency variant is apg_solve_latency");
     const int lane = c.lane;
     const int n = P.H * NU;
     const float invP = __fdiv_rn(1.0f, (float)PP);
     for (int i = lane; i < n; i += 32) c.yk[i] = c.xk[i];
     __syncwarp();
     float Jx = 0.f, Jp = 0.f, fy = 0.f, gsq = 0.f, sum_ls = 0.f, sum_s = 0.f, init_cost = 0.f;
-    int k = 1, no_improve = 0, it = 0, ls_round = 0;
-    (void)ls_round;
+    int k = 1, no_improve = 0, it = 0;
     for (;;) {
         ++it;
         {
@@ -907,55 +902,6 @@ __device__ __forceinline__ void apg_solve(const KParams& P, Warp<NU, W>& c, cons
                 if (ok) break;
                 if (j < P.maxls) s = s * P.dec_f;
             }
-        } else {
-            // rounds of LSW concurrent trials: trial index j = base + l; a later round only runs when every
-            // trial of the earlier rounds failed, so the selected trial is the first passing one, as in the
-            // sequential search.  Steps are s*dec^j built by the same chain of multiplications.
-            const int l = tm.ls_index;
-            const float s0 = s;
-            float s_base = s;
-            int base = 0, jsel = 0;
-            float* slot = nullptr;
-            for (;;) {
-                const int j = base + l;
-                float s_l = s_base;
-                for (int q = 0; q < l; ++q) s_l = s_l * P.dec_f;
-                slot = tm.scratch + 2 * LSW * (ls_round & 1);   // double buffered: one barrier per round
-                ++ls_round;
-                if (j <= P.maxls) {
-                    float part = 0.f;
-                    for (int i = lane; i < n; i += 32) {
-                        const int ii = i % NU;
-                        const float gi = c.g[i], yi = c.yk[i];
-                        const float xv = clipf(fma_(-s_l, gi, yi), P.u_lo[ii], P.u_hi[ii]);
-                        c.xp[i] = xv;
-                        part = fma_(gi, xv - yi, part);
-                    }
-                    const float dec = warp_butterfly(part);
-                    __syncwarp();
-                    const float Jl = rollout_fwd<NU, W, 0>(P, c, c.xp, x0) * invP;
-                    if (lane == 0) { slot[2 * l] = Jl; slot[2 * l + 1] = (Jl <= fma_(P.coef, dec, fy)) ? 1.f : 0.f; }
-                }
-                asm volatile("bar.sync %0, %1;" ::"r"(tm.ls_bar_id), "r"(LSW * 32) : "memory");
-                int q = 0;
-                for (; q < LSW && base + q <= P.maxls; ++q)
-                    if (slot[2 * q + 1] != 0.f) { ok = true; break; }
-                if (ok) { jsel = base + q; break; }
-                if (base + LSW > P.maxls) { jsel = P.maxls; break; }   // every trial failed
-                for (int r = 0; r < LSW; ++r) s_base = s_base * P.dec_f;
-                base += LSW;
-            }
-            s = s0;
-            for (int q = 0; q < jsel; ++q) s = s * P.dec_f;
-            Jp = slot[2 * (jsel - base)];
-            n_ls = jsel + 1;
-            if (jsel != base + l) {   // adopt the selected trial point (same arithmetic as the warp that evaluated it)
-                for (int i = lane; i < n; i += 32) {
-                    const int ii = i % NU;
-                    c.xp[i] = clipf(fma_(-s, c.g[i], c.yk[i]), P.u_lo[ii], P.u_hi[ii]);
-                }
-            }
-            __syncwarp();
         }
         sum_ls = sum_ls + (float)n_ls;
         sum_s = sum_s + s;

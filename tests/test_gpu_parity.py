@@ -255,6 +255,15 @@ def test_closed_loop_monte_carlo(solver, O):
     xh, uh, st = s.closed_loop(x0, t0, rng, ticks)
     xho, uho, sto = o.closed_loop(x0, t0, rng, ticks)
     _eq(uh, uho, "applied controls"); _eq(xh, xho, "plant trajectory"); _eq(st, sto, "stats")
+    # 80 rollouts: one-SM latency kernel; 160 rollouts: one warp per rollout
+    cfgs, ss, os_ = _pair(solver, O, "iris", "traj", max_iter=4, rtol=0.0, atol=0.0)
+    ss.set_trajectory(tab); os_.set_trajectory(tab)
+    for R2 in (80, 160):
+        x2 = synthetic.initial_states(tab[0, 1:4], R2, seed=6)
+        t2 = np.linspace(0, 5, R2).astype(np.float32)
+        r2 = np.array([[900 + r, 7] for r in range(R2)], np.uint64)
+        a, b = ss.closed_loop(x2, t2, r2, 3), os_.closed_loop(x2, t2, r2, 3)
+        _eq(a[0], b[0], f"R={R2} plant trajectory"); _eq(a[1], b[1], f"R={R2} controls"); _eq(a[2], b[2], f"R={R2} stats")
     # P = 8 variant
     cfg8, s8, o8 = _pair(solver, O, "iris", "traj", max_iter=6, num_particles=8, rtol=0.0, atol=0.0)
     s8.set_trajectory(tab); o8.set_trajectory(tab)
