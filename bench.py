@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="problems per GPU per step")
     ap.add_argument("--max-iter", type=int, default=200)
-    ap.add_argument("--latency-ticks", type=int, default=300)
+    ap.add_argument("--latency-ticks", type=int, default=1000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
     args = ap.parse_args()
@@ -296,7 +296,7 @@ def main():
         up, ip = s1.reset(1)
         rng1 = np.array([[10, 0]], np.uint64)
         e2e_l, dev_l = [], []
-        n_warm = 20
+        n_warm = 100
         for k in range(n_warm + args.latency_ticks):
             ct = np.array([0.05 * k], np.float32)
             t = time.perf_counter()
