@@ -82,6 +82,66 @@ __device__ __forceinline__ float2 det_tanh2(float2 x) {
     return make_float2(copysignf(th.x, x.x), copysignf(th.y, x.y));
 }
 
+// exp of both halves, x <= 0 (same per-component sequence as det_exp_nonpos)
+__device__ __forceinline__ float2 det_exp_nonpos2(float2 x) {
+    x.x = x.x < -80.0f ? -80.0f : x.x;
+    x.y = x.y < -80.0f ? -80.0f : x.y;
+    float2 t = mul2_(x, splat(1.44269504f));
+    float2 n = add2_(add2_(t, splat(12582912.0f)), splat(-12582912.0f));
+    float2 r = fma2_(n, splat(-0.693359375f), x);
+    r = fma2_(n, splat(2.12194440e-4f), r);
+    float2 p = splat(1.38888889e-3f);
+    p = fma2_(p, r, splat(8.33333333e-3f));
+    p = fma2_(p, r, splat(4.16666667e-2f));
+    p = fma2_(p, r, splat(1.66666667e-1f));
+    p = fma2_(p, r, splat(0.5f));
+    p = fma2_(p, r, splat(1.0f));
+    p = fma2_(p, r, splat(1.0f));
+    float2 e;
+    e.x = __uint_as_float(__float_as_uint(p.x) + (((uint32_t)__float2int_rz(n.x)) << 23));
+    e.y = __uint_as_float(__float_as_uint(p.y) + (((uint32_t)__float2int_rz(n.y)) << 23));
+    return e;
+}
+
+// softplus and (optionally) sigmoid of both halves; per component the same sequence as det_softplus_sigmoid
+__device__ __forceinline__ void det_softplus_sigmoid2(float2 s, float2& sp, float2& sg, bool want_sg) {
+    const float2 e = det_exp_nonpos2(make_float2(-fabsf(s.x), -fabsf(s.y)));
+    const float2 d = add2_(splat(1.0f), e);
+    const bool bx = d.x > 1.41421356f, by = d.y > 1.41421356f;
+    float2 m;
+    m.x = bx ? __fmul_rn(d.x, 0.5f) : d.x;
+    m.y = by ? __fmul_rn(d.y, 0.5f) : d.y;
+    const float2 f = add2_(m, splat(-1.0f));
+    float2 p = splat(7.0376836292e-2f);
+    p = fma2_(p, f, splat(-1.1514610310e-1f));
+    p = fma2_(p, f, splat(1.1676998740e-1f));
+    p = fma2_(p, f, splat(-1.2420140846e-1f));
+    p = fma2_(p, f, splat(1.4249322787e-1f));
+    p = fma2_(p, f, splat(-1.6668057665e-1f));
+    p = fma2_(p, f, splat(2.0000714765e-1f));
+    p = fma2_(p, f, splat(-2.4999993993e-1f));
+    p = fma2_(p, f, splat(3.3333331174e-1f));
+    const float2 z = mul2_(f, f);
+    float2 y = mul2_(mul2_(f, z), p);
+    y = fma2_(splat(-0.5f), z, y);
+    y = add2_(f, y);
+    y.x = bx ? __fadd_rn(y.x, 0.693147181f) : y.x;
+    y.y = by ? __fadd_rn(y.y, 0.693147181f) : y.y;
+    sp = add2_(make_float2(s.x > 0.0f ? s.x : 0.0f, s.y > 0.0f ? s.y : 0.0f), y);
+    if (want_sg) {
+        float2 q = fma2_(splat(-0.470588235f), d, splat(1.41176471f));
+        const float2 nd = make_float2(-d.x, -d.y);
+        float2 err = fma2_(nd, q, splat(1.0f)); q = fma2_(q, err, q);
+        err = fma2_(nd, q, splat(1.0f)); q = fma2_(q, err, q);
+        err = fma2_(nd, q, splat(1.0f)); q = fma2_(q, err, q);
+        const float2 eq = mul2_(e, q);
+        sg.x = s.x >= 0.0f ? q.x : eq.x;
+        sg.y = s.y >= 0.0f ? q.y : eq.y;
+    } else {
+        sg = splat(0.f);
+    }
+}
+
 // cephes logf kernel on f = m - 1, m in [sqrt(1/2), sqrt(2)]
 __device__ __forceinline__ float det_log_kernel(float f) {
     float p = 7.0376836292e-2f;

@@ -430,15 +430,26 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
             }
         }
         const float s0 = P.sig0[o >= 6 ? o - 6 : 0];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            const float out = (aA[p].x + aA[p].y) + (aB[p].x + aB[p].y);
-            float sp, sg;
-            det_softplus_sigmoid(out, sp, sg);
-            if (lane < 6) ob[p][lane] = out;
+        if constexpr (NP == 2) {   // the two problems' softplus / sigmoid packed into FFMA2
+            const float2 out = make_float2((aA[0].x + aA[0].y) + (aB[0].x + aB[0].y), (aA[1].x + aA[1].y) + (aB[1].x + aB[1].y));
+            float2 sp, sg;
+            det_softplus_sigmoid2(out, sp, sg, tape);
+            if (lane < 6) { ob[0][lane] = out.x; ob[1][lane] = out.y; }
             else if (lane < 12) {
-                ob[p][lane] = s0 * sp;
-                if (tape) ob[p][lane + 6] = s0 * sg;
+                ob[0][lane] = s0 * sp.x; ob[1][lane] = s0 * sp.y;
+                if (tape) { ob[0][lane + 6] = s0 * sg.x; ob[1][lane + 6] = s0 * sg.y; }
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                const float out = (aA[p].x + aA[p].y) + (aB[p].x + aB[p].y);
+                float sp, sg;
+                det_softplus_sigmoid(out, sp, sg);
+                if (lane < 6) ob[p][lane] = out;
+                else if (lane < 12) {
+                    ob[p][lane] = s0 * sp;
+                    if (tape) ob[p][lane + 6] = s0 * sg;
+                }
             }
         }
     }
