@@ -193,6 +193,56 @@ def test_nondefault_schedule_and_options(solver, O, mode):
     assert len(set(a[2][:, 2])) > 1         # early stops (no-improvement budget) at different iterations
 
 
+@pytest.mark.parametrize("seed", list(range(24)))
+def test_randomised_configurations(solver, O, seed):
+    """Seeded fuzz over the configuration space (horizon 4..32, step grid, discount, cost weights, bounds, line-search
+    constants, maxls 0..6, particles, vehicle, frame, batch size -> kernel choice): solve + value_and_grad stay
+    bit-identical to the oracle."""
+    import os
+
+    from conftest import ROOT
+    from sde4mbrl_px4_b200 import config, model_io
+
+    rng = np.random.default_rng(1000 + seed)
+    vehicle = ["iris", "hexa"][seed % 2]
+    P = int(rng.choice([1, 1, 2, 4, 8])) if vehicle == "iris" else int(rng.choice([1, 8]))
+    cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{vehicle}_traj.yaml"))
+    H = int(rng.integers(4, 33))
+    nu = 4 if vehicle == "iris" else 6
+    cfgd.update(horizon=H, num_short_dt=int(rng.integers(0, H + 1)), short_step_dt=float(rng.uniform(0.02, 0.06)),
+                long_step_dt=float(rng.uniform(0.05, 0.12)), discount=float(rng.uniform(0.9, 1.0)), num_particles=P)
+    cp = cfgd["cost_params"]
+    for k in ("perr", "verr", "qerr", "werr"):
+        cp[k] = [float(v) for v in rng.uniform(0.1, 150.0, 3)]
+    cp.update(uerr=float(rng.uniform(0, 2)), res_mult=float(rng.uniform(0, 0.5)), u_slew_coeff=float(rng.uniform(0, 2)),
+              uref=[float(v) for v in rng.uniform(0.3, 0.8, nu)])
+    lo = rng.uniform(1e-4, 0.2, nu)
+    cfgd["input_constr"]["input_bound"] = [[float(a), float(b)] for a, b in zip(lo, rng.uniform(0.85, 1.0, nu))]
+    ls = cfgd["apg_mpc"]["linesearch"]
+    ls.update(maxls=int(rng.integers(0, 7)), init_stepsize=float(10 ** rng.uniform(-5, -2)), coef=float(rng.uniform(0.001, 0.3)),
+              decrease_factor=float(rng.uniform(0.3, 0.8)), increase_factor=float(rng.uniform(1.0, 2.0)),
+              max_stepsize=float(10 ** rng.uniform(-4, 0)), reset_option=str(rng.choice(["increase", "conservative"])))
+    cfgd["apg_mpc"].update(max_iter=int(rng.integers(3, 25)), max_no_improvement_iter=int(rng.integers(1, 6)),
+                           rtol=float(rng.choice([0.0, 1e-4])), atol=float(rng.choice([0.0, 1e-3])))
+    kernel_flags = [{}, {"group": True}, {"sequential_ls": True}, {"speculative_ls": True}, {"no_cluster": True}][seed % 5]
+    cfg = config.build_config(cfgd, convert_to_enu=bool(seed % 3), no_shift=bool(seed % 4 == 1), **kernel_flags)
+    blob = model_io.synthetic_model(vehicle, seed=seed, weight_scale=float(rng.uniform(0.05, 0.6))).to_blob()
+    s, o = solver.MPCSolver(cfg, blob), O.Oracle(cfg, blob, "f32")
+    B = int(rng.choice([1, 3, 37, 160]))
+    pr = synthetic.batched_problems(B, H, np.array(cfg.dt[:H]), seed=seed)
+    u0, i0 = s.reset(B)
+    u0 = np.clip(u0 + 0.1 * rng.standard_normal(u0.shape), 1e-4, 1).astype(np.float32)
+    i0[:, 1] = rng.choice([cfg.init_stepsize, 2e-6], B)
+    a = s.rollout(pr["x"], u0, u0[:, 0], xref_win=pr["xref_win"], rng=pr["rng"])
+    b = o.rollout(pr["x"], u0, u0[:, 0], xref_win=pr["xref_win"], rng=pr["rng"])
+    for x, y, w in zip(a, b, ("cost", "grad", "x_evol")):
+        _eq(x, y, f"{w} seed {seed}")
+    a = s.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+    b = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+    _eq(a[3], b[3], f"trace seed {seed}"); _eq(a[0], b[0], f"u* seed {seed}"); _eq(a[1], b[1], f"x_evol seed {seed}")
+    _eq(a[2][:, :7], b[2][:, :7], f"telemetry seed {seed}")
+
+
 def test_early_stopping_with_yaml_tolerances(solver, O):
     """Default YAML tolerances (rtol 1e-6, atol 1e-8): per-problem iteration counts differ and still match."""
     cfg, s, o = _pair(solver, O, "iris", "pos")
