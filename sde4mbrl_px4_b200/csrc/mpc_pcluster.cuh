@@ -1,0 +1,181 @@
+// mpc_pcluster.cuh — latency kernel for P > 1 particles: one problem per thread-block cluster.
+//
+// The P particle rollouts of a problem are independent given the control sequence, and so are the line-search
+// trials of an iteration.  A cluster of P*LSW/4 CTAs (4 warps each, one per SM sub-partition, so that no two
+// warps share an issue port) holds LSW replicas x P particles of ONE problem: warp (l, p) integrates particle p;
+// in the gradient phase all replicas do the same work, in the line search replica l evaluates trial base + l.
+// Particle means (cost: sequential sum in particle order times 1/P; gradient likewise) and the per-trial
+// (J, slope) pairs are exchanged through distributed shared memory with two cluster barriers per iteration.
+// Same SPEC-ARITH sequences as every other kernel: bit-identical results.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "mpc_kernels.cuh"
+
+namespace sdempc {
+
+template <int PP, int LSW>
+struct PCluster {
+    static constexpr int TW = PP * LSW;   // warps of the team
+    static constexpr int CS = TW / 4;     // CTAs of the cluster
+    int l, p, gwi;                        // replica, particle, warp index in the team
+    float* xc_local;                      // this CTA's exchange area: [2 parities][4 warps][2 floats]
+    float* warp_base_local;               // this CTA's per-warp regions
+    int ws_stride;
+    __device__ __forceinline__ void barrier() const {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+    // exchange slot / region of team warp `w` (possibly in another CTA of the cluster)
+    __device__ __forceinline__ const float* slot(int w, int parity) const {
+        const float* loc = xc_local + (parity * 4 + (w & 3)) * 2;
+        return cooperative_groups::this_cluster().map_shared_rank(loc, w >> 2);
+    }
+    __device__ __forceinline__ const float* region(int w) const {
+        const float* loc = warp_base_local + (size_t)(w & 3) * ws_stride;
+        return cooperative_groups::this_cluster().map_shared_rank(loc, w >> 2);
+    }
+};
+
+// publish (a, b) of this warp, barrier, return every team warp's pair: lane w (< TW) holds warp w's pair
+template <int PP, int LSW>
+__device__ __forceinline__ float2 pc_exchange(const PCluster<PP, LSW>& pc, int lane, int warp_in_cta, int parity, float a, float b) {
+    if (lane == 0) {
+        float* s = pc.xc_local + (parity * 4 + warp_in_cta) * 2;
+        s[0] = a; s[1] = b;
+    }
+    pc.barrier();
+    float2 v = make_float2(0.f, 0.f);
+    if (lane < PCluster<PP, LSW>::TW) { const float* s = pc.slot(lane, parity); v.x = s[0]; v.y = s[1]; }
+    return v;
+}
+
+// mean over the particles of replica r of the .x components (sequential sum in particle order, times 1/P)
+template <int PP>
+__device__ __forceinline__ float pc_replica_mean(float vx, int r, float invP) {
+    float acc = __shfl_sync(0xffffffffu, vx, r * PP);
+#pragma unroll
+    for (int q = 1; q < PP; ++q) acc = acc + __shfl_sync(0xffffffffu, vx, r * PP + q);
+    return acc * invP;
+}
+
+template <int NU, int W, int PP, int LSW>
+__device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>& c, const PCluster<PP, LSW>& pc, int warp_in_cta,
+                                                   const float (&x0)[NX], float s, sdempc_info& inf, float* trace) {
+    const int lane = c.lane;
+    const int n = P.H * NU;
+    const float invP = __fdiv_rn(1.0f, (float)PP);
+    const int l = pc.l;
+    for (int i = lane; i < n; i += 32) c.yk[i] = c.xk[i];
+    __syncwarp();
+    float Jx = 0.f, Jp = 0.f, fy = 0.f, gsq = 0.f, sum_ls = 0.f, sum_s = 0.f, init_cost = 0.f;
+    int k = 1, no_improve = 0, it = 0, xpar = 0;
+    for (;;) {
+        ++it;
+        {   // gradient at y_k: this warp's particle, then the particle mean of this replica
+            float* gsave = c.g;
+            c.g = c.g2;
+            const float Jw = rollout_fwd<NU, W, 1>(P, c, c.yk, x0);
+            rollout_bwd<NU, W>(P, c, c.yk);
+            c.g = gsave;
+            const float2 v = pc_exchange<PP, LSW>(pc, lane, warp_in_cta, xpar, Jw, 0.f);
+            xpar ^= 1;
+            fy = pc_replica_mean<PP>(v.x, l, invP);
+            for (int i = lane; i < n; i += 32) {
+                float a = pc.region(l * PP)[P.o_g2 + i];
+#pragma unroll
+                for (int q = 1; q < PP; ++q) a = a + pc.region(l * PP + q)[P.o_g2 + i];
+                c.g[i] = a * invP;
+            }
+            __syncwarp();
+        }
+        if (it == 1) { Jx = fy; init_cost = fy; }
+        {
+            float part = 0.f;
+            for (int i = lane; i < n; i += 32) { const float gi = c.g[i]; part = fma_(gi, gi, part); }
+            gsq = warp_butterfly(part);
+        }
+        if (P.reset_option == 1) { s = s * P.inc_f; s = s > P.max_step ? P.max_step : s; }
+        const float s0 = s;
+        bool ok = false;
+        int jsel = 0, base = 0;
+        float s_base = s0;
+        for (;;) {   // rounds of LSW concurrent trials
+            const int j = base + l;
+            float Jw = 0.f, dec = 0.f;
+            if (j <= P.maxls) {
+                float s_l = s_base;
+                for (int q = 0; q < l; ++q) s_l = s_l * P.dec_f;
+                float part = 0.f;
+                for (int i = lane; i < n; i += 32) {
+                    const int ii = i % NU;
+                    const float gi = c.g[i], yi = c.yk[i];
+                    const float xv = clipf(fma_(-s_l, gi, yi), P.u_lo[ii], P.u_hi[ii]);
+                    c.xp[i] = xv;
+                    part = fma_(gi, xv - yi, part);
+                }
+                dec = warp_butterfly(part);
+                __syncwarp();
+                Jw = rollout_fwd<NU, W, 0>(P, c, c.xp, x0);
+            }
+            const float2 v = pc_exchange<PP, LSW>(pc, lane, warp_in_cta, xpar, Jw, dec);
+            xpar ^= 1;
+            int q = 0;
+            float Jq = 0.f;
+            for (; q < LSW && base + q <= P.maxls; ++q) {
+                Jq = pc_replica_mean<PP>(v.x, q, invP);
+                const float dq = __shfl_sync(0xffffffffu, v.y, q * PP);
+                if (Jq <= fma_(P.coef, dq, fy)) { ok = true; break; }
+            }
+            if (ok) { jsel = base + q; Jp = Jq; break; }
+            if (base + LSW > P.maxls) { jsel = P.maxls; Jp = Jq; break; }   // every trial failed: Jq is the last trial's cost
+            for (int r = 0; r < LSW; ++r) s_base = s_base * P.dec_f;
+            base += LSW;
+        }
+        s = s0;
+        for (int q = 0; q < jsel; ++q) s = s * P.dec_f;
+        const int n_ls = jsel + 1;
+        for (int i = lane; i < n; i += 32) {
+            const int ii = i % NU;
+            c.xp[i] = clipf(fma_(-s, c.g[i], c.yk[i]), P.u_lo[ii], P.u_hi[ii]);
+        }
+        __syncwarp();
+        sum_ls = sum_ls + (float)n_ls;
+        sum_s = sum_s + s;
+        const bool accept = ok && (Jp <= Jx);
+        bool converged = false;
+        if (accept) {
+            const float beta = __fdiv_rn((float)k, (float)(k + 3));
+            for (int i = lane; i < n; i += 32) {
+                const int ii = i % NU;
+                const float xv = c.xp[i];
+                c.yk[i] = clipf(fma_(beta, xv - c.xk[i], xv), P.u_lo[ii], P.u_hi[ii]);
+                c.xk[i] = xv;
+            }
+            const float Jprev = Jx;
+            Jx = Jp; ++k; no_improve = 0;
+            const float tol = P.atol + P.rtol * fabsf(Jprev);
+            converged = (fabsf(Jprev - Jx) <= tol) || (Jx <= P.atol);
+        } else {
+            for (int i = lane; i < n; i += 32) c.yk[i] = c.xk[i];
+            k = 1; ++no_improve;
+        }
+        __syncwarp();
+        if (trace != nullptr && pc.gwi == 0 && lane == 0) {
+            float* tr = trace + (size_t)(it - 1) * SDEMPC_TRACE_W;
+            tr[0] = fy; tr[1] = Jp; tr[2] = s; tr[3] = (float)n_ls; tr[4] = accept ? 1.f : 0.f; tr[5] = Jx; tr[6] = gsq; tr[7] = (float)k;
+        }
+        if (it >= P.max_iter || no_improve >= P.max_no_improve || converged || !(fy == fy)) break;
+    }
+    (void)rollout_fwd<NU, W, 2>(P, c, c.xk, x0);
+    __syncwarp();
+    inf.avg_linesearch = __fdiv_rn(sum_ls, (float)it);
+    inf.stepsize = s;
+    inf.num_steps = (float)it;
+    inf.grad_sqr = gsq;
+    inf.avg_stepsize = __fdiv_rn(sum_s, (float)it);
+    inf.init_cost = init_cost;
+    inf.opt_cost = (Jx == Jx) ? Jx : __int_as_float(0x7f800000);
+    inf.solve_time_us = 0.f;
+}
+
+}  // namespace sdempc

@@ -19,6 +19,7 @@
 
 #include "mpc_group.cuh"
 #include "mpc_kernels.cuh"
+#include "mpc_pcluster.cuh"
 
 using namespace sdempc;
 
@@ -309,6 +310,115 @@ __global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) 
     if constexpr (CL) cooperative_groups::this_cluster().sync();   // keep shared memory alive for the sibling CTA
 }
 
+// Latency kernel for P > 1 (mpc_pcluster.cuh): one problem per cluster of PP*LSW/4 CTAs, 4 warps per CTA.
+template <int NU, int W, int PP, int LSW>
+__global__ void __launch_bounds__(128, 1) mpc_pcluster_kernel(const __grid_constant__ KParams P) {
+    using L = Layout<NU, W>;
+    using PC = PCluster<PP, LSW>;
+    extern __shared__ __align__(128) float smem[];
+    float* ws = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::SMEM_FLOATS);
+    float* team_base = smem + L::SMEM_FLOATS + 4;
+    float* warp_base = team_base + P.team_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto cluster = cooperative_groups::this_cluster();
+    const int crank = (int)cluster.block_rank();
+
+    stage_weights<L::SMEM_FLOATS * 4>(ws, P.wimg, bar);
+
+    Warp<NU, W> c;
+    c.lane = lane;
+    c.ws = ws;
+    float* wb = warp_base + (size_t)warp * P.ws_stride;
+    c.xk = wb + P.o_xk; c.yk = wb + P.o_yk; c.g = wb + P.o_g; c.g2 = wb + P.o_g2; c.xp = wb + P.o_xp; c.uprev = wb + P.o_uprev;
+    c.xref = wb + P.o_xref; c.xi = wb + P.o_xi; c.xtape = wb + P.o_xtape; c.stape = wb + P.o_stape;
+    c.bufA = wb + P.o_bufA; c.bufB = wb + P.o_bufB; c.act3 = wb + P.o_act3; c.lz = wb + P.o_lz; c.red = wb + P.o_red;
+    if (P.mtape_g != nullptr) c.mtape = P.mtape_g + ((size_t)blockIdx.x * 4 + warp) * (size_t)P.H * 2 * W;
+    else c.mtape = reinterpret_cast<float2*>(wb + P.o_mtape);
+    c.load_regs(P.wimg);
+
+    PC pc;
+    pc.gwi = crank * 4 + warp;
+    pc.l = pc.gwi / PP;
+    pc.p = pc.gwi % PP;
+    pc.xc_local = team_base;
+    pc.warp_base_local = warp_base;
+    pc.ws_stride = P.ws_stride;
+
+    mbar_wait(bar, 0);
+    cluster.sync();   // every CTA of the cluster resident before any DSMEM access
+
+    const int n = P.H * NU;
+    const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
+    for (int b = (int)(blockIdx.x / PC::CS); b < P.B; b += (int)(gridDim.x / PC::CS)) {
+        float x0[NX];
+        {
+            float tmp[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) tmp[i] = __ldg(P.x + (size_t)b * NX + i);
+            if (enu) enu_ned(tmp, x0);
+            else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) x0[i] = tmp[i];
+            }
+        }
+        build_window(P, lane, c.xref, P.xref_win ? P.xref_win + (size_t)b * (P.H + 1) * NX : nullptr,
+                     P.curr_t ? P.curr_t + b : nullptr, P.xdes ? P.xdes + (size_t)b * NX : nullptr, 0.f, false);
+        if (P.xi_override != nullptr) {
+            if (lane < P.H) {
+                const float* src = P.xi_override + (((size_t)b * PP + pc.p) * P.H + lane) * 6;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) c.xi[lane * 8 + i] = __ldg(src + i);
+            }
+        } else {
+            gen_noise(lane, P.rng[2 * (size_t)b], P.rng[2 * (size_t)b + 1], (uint32_t)pc.p, 0u, P.H, c.xi);
+        }
+        const float* pin = P.u_plan + (size_t)b * n;
+        if (lane < NU) c.uprev[lane] = __ldg(pin + lane);
+        for (int i = lane; i < n; i += 32) {
+            const int t = i / NU, ii = i % NU;
+            const int ts = (P.flags & SDEMPC_F_NO_SHIFT) ? t : (t + 1 < P.H ? t + 1 : P.H - 1);
+            c.xk[i] = clipf(__ldg(pin + ts * NU + ii), P.u_lo[ii], P.u_hi[ii]);
+        }
+        __syncwarp();
+        float s = P.info[b].stepsize;
+        s = s > 0.f ? s : P.init_step;
+        sdempc_info inf;
+        apg_solve_pcluster<NU, W, PP, LSW>(P, c, pc, warp, x0, s, inf,
+                                           P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
+        if (pc.gwi == 0) {
+            for (int i = lane; i < n; i += 32) P.u_plan_out[(size_t)b * n + i] = c.xk[i];
+            if (lane == 0) P.info_out[b] = inf;
+        }
+        pc.barrier();   // every particle's state tape complete
+        if (pc.gwi == 0 && lane <= P.H) {
+            const float invP = __fdiv_rn(1.0f, (float)PP);
+            float row[NX], o[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) row[i] = pc.region(0)[P.o_xtape + lane * 16 + i];
+#pragma unroll
+            for (int q = 1; q < PP; ++q) {
+                const float* rq = pc.region(q) + P.o_xtape + lane * 16;
+#pragma unroll
+                for (int i = 0; i < NX; ++i) row[i] = row[i] + rq[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) row[i] = row[i] * invP;
+            quat_renorm(row + 6);
+            if (enu) enu_ned(row, o);
+            else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) o[i] = row[i];
+            }
+            float* dst = P.x_evol + (size_t)b * (P.H + 1) * NX + lane * NX;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) dst[i] = o[i];
+        }
+        pc.barrier();   // tapes may be overwritten by the next problem
+    }
+    cluster.sync();
+}
+
 // Throughput kernel: GW warps per CTA, each warp owns GP problems (mpc_group.cuh).  P = 1.
 template <int NU, int W, int GP, int GW>
 __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_constant__ KParams P) {
@@ -449,6 +559,7 @@ struct KernelChoice {
     void (*closed_spec)(KParams);
     void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
     void (*closed_cl)(KParams);
+    void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x GROUP_GP problems per CTA (P == 1, W == 32)
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
@@ -466,6 +577,8 @@ static KernelChoice make_choice() {
     k.closed_spec = nullptr;
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
+    k.solve_pc = nullptr;
+    if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
     if constexpr (PP == 1 && W == 32) k.solve_group = mpc_group_kernel<NU, W, GROUP_GP, GROUP_GW>;
     if constexpr (PP == 1) {
         k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW, SPEC_SGW>;
@@ -522,7 +635,7 @@ struct sdempc_handle {
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false;
     float last_ms = 0.f;
 };
 
@@ -667,6 +780,8 @@ static int ensure_device(sdempc_handle* h) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.closed_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl));
     }
+    if (h->kc.solve_pc)
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_pc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl));
     if (h->kc.solve_group) {
         if (h->smem_bytes_group > (size_t)prop.sharedMemPerBlockOptin) h->kc.solve_group = nullptr;   // does not fit: use one warp per problem
         else CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_group));
@@ -693,6 +808,13 @@ static bool use_spec(const sdempc_handle* h, int B) {
 // cluster variant of the latency kernel: two SMs per problem
 static bool use_cluster(const sdempc_handle* h, int B) {
     return use_spec(h, B) && h->kc.solve_cl != nullptr && 2 * B <= h->sm_count && !(h->cfg.flags & SDEMPC_F_NO_CLUSTER);
+}
+
+// P > 1: particle cluster (P * SPEC_LSW / 4 SMs per problem)
+static bool use_pcluster(const sdempc_handle* h, int B) {
+    if (h->kc.solve_pc == nullptr || h->cfg.maxls < 1) return false;
+    if (h->cfg.flags & (SDEMPC_F_SEQUENTIAL_LS | SDEMPC_F_NO_CLUSTER)) return false;
+    return B * (h->kc.P * SPEC_LSW / 4) <= h->sm_count;
 }
 
 static bool use_group(const sdempc_handle* h, int B) {
@@ -792,8 +914,8 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
     const bool spec = use_spec(h, B), group = use_group(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
-    const bool cl = use_cluster(h, B);
-    const int grid = cl ? 2 * B : spec ? std::min(B, h->sm_count)
+    const bool cl = use_cluster(h, B), pcl = use_pcluster(h, B);
+    const int grid = pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
     if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
     else if ((rc = ensure_mtape(h, grid))) return rc;
@@ -825,12 +947,13 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
-    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl;
+    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl;
     return 0;
 }
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
-    if (fn != nullptr && (fn == h->kc.solve_cl || fn == h->kc.closed_cl)) {   // 2-CTA cluster per problem
+    if (fn != nullptr && (fn == h->kc.solve_cl || fn == h->kc.closed_cl || fn == h->kc.solve_pc)) {   // one cluster per problem
+        const unsigned cs = (fn == h->kc.solve_pc) ? (unsigned)(h->kc.P * SPEC_LSW / 4) : 2u;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(SPEC_LSW * 32);
@@ -838,7 +961,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         CUDA_TRY(cudaLaunchKernelEx(&cfg, fn, k));
@@ -1015,7 +1138,7 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     for (int i = 0; i < n; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch(h, h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
+        int rc = launch(h, h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -1056,7 +1179,7 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     int rc = stage_solve(h, a);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
+    if ((rc = launch(h, h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
     float t = 0.f;
@@ -1171,9 +1294,9 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
-    out[0] = h->staged_cl ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    out[0] = (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
-    out[2] = h->staged_spec ? 1 : h->staged_group ? GROUP_GW * GROUP_GP : h->kc.G;
+    out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * GROUP_GP : h->kc.G;
     out[3] = h->regs;
     out[4] = h->last_grid;
     out[5] = h->sm_count;

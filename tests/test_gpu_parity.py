@@ -163,6 +163,24 @@ def test_three_kernels_agree(solver, O, vehicle, width):
         _eq(info[:, :7], infoo[:n, :7], f"telemetry {mode}"); _eq(tr, tro[:n], f"trace {mode}")
 
 
+@pytest.mark.parametrize("vehicle,P", [("iris", 2), ("iris", 4), ("iris", 8), ("hexa", 8)])
+def test_particle_cluster_kernel(solver, O, vehicle, P):
+    """P > 1 latency kernel (one problem per cluster of P CTAs: 4 replicas x P particle warps, DSMEM exchange of the
+    particle means and line-search results) against the team kernel (P warps in one CTA) and the oracle."""
+    ov = dict(num_particles=P, max_iter=25)
+    cfg, s, o = _pair(solver, O, vehicle, "traj", **ov)
+    B = 3
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=40 + P)
+    u0, i0 = s.reset(B)
+    b = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+    for mode, threads in ((dict(), 128), (dict(sequential_ls=True), 256)):
+        _, sm, _ = _pair(solver, O, vehicle, "traj", **ov, **mode)
+        a = sm.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
+        assert sm.kernel_info()["threads_per_cta"] == threads, sm.kernel_info()
+        _eq(a[3], b[3], f"trace {mode}"); _eq(a[0], b[0], f"u* {mode}"); _eq(a[1], b[1], f"x_evol {mode}")
+        _eq(a[2][:, :7], b[2][:, :7], f"telemetry {mode}")
+
+
 @pytest.mark.parametrize("mode", [{}, {"group": True}, {"sequential_ls": True}])
 def test_nondefault_schedule_and_options(solver, O, mode):
     """Horizon 12 with a short/long step grid, discount < 1, conservative step-size reset, maxls = 6 (two rounds
