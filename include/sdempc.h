@@ -59,8 +59,9 @@ extern "C" {
 #define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
 #define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
 #define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a 2-CTA cluster */
-/* Default kernel choice: latency kernel when B <= number of SMs, throughput kernel above (P = 1, width 32),
- * one warp per problem otherwise.  All three produce bit-identical results. */
+/* Default kernel choice: latency kernels when the batch fits one problem per SM (or per cluster), the throughput
+ * kernel for large batches (> ~13 problems per SM; P = 1, width 32), one warp per (problem, particle) otherwise.
+ * All of them produce bit-identical results. */
 
 /*
  * Solver configuration == the YAML schema of launch/iris_sitl_traj_mpc.yaml:1-85

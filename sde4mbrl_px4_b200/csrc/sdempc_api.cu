@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) 
     const int n = P.H * NU;
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
 
-    const int b_first = CL ? (int)(blockIdx.x / 2) : (int)(blockIdx.x * G + team);
+    // one warp (team) per problem: problems are dealt across CTAs first, so a small batch spreads over all SMs
+    const int b_first = CL ? (int)(blockIdx.x / 2) : (int)(team * gridDim.x + blockIdx.x);
     const int b_step = CL ? (int)(gridDim.x / 2) : (int)(gridDim.x * G);
     for (int b = b_first; b < P.B; b += b_step) {
         // ---- state ----
@@ -794,8 +795,7 @@ static int ensure_device(sdempc_handle* h) {
 }
 
 static int grid_for(const sdempc_handle* h, int B) {
-    const int ctas = (B + h->kc.G - 1) / h->kc.G;
-    return std::max(1, std::min(ctas, h->sm_count));   // one persistent CTA per SM at most
+    return std::max(1, std::min(B, h->sm_count));   // one persistent CTA per SM at most; problems dealt across CTAs first
 }
 
 static bool use_spec(const sdempc_handle* h, int B) {
@@ -818,8 +818,9 @@ static bool use_pcluster(const sdempc_handle* h, int B) {
 }
 
 static bool use_group(const sdempc_handle* h, int B) {
+    // measured crossover against one warp per problem (tools/batch_sweep.py): ~13 problems per SM
     return h->kc.solve_group != nullptr && !(h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) && !use_spec(h, B) &&
-           ((h->cfg.flags & SDEMPC_F_GROUP) != 0 || B > h->sm_count);
+           ((h->cfg.flags & SDEMPC_F_GROUP) != 0 || B > 13 * h->sm_count);
 }
 
 static int ensure_mtape_group(sdempc_handle* h, int grid) {

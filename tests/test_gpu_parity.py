@@ -157,7 +157,7 @@ def test_three_kernels_agree(solver, O, vehicle, width):
         assert ki["threads_per_cta"] == (256 if threads == 255 else threads), (mode, ki)
         if threads in (255, 128):
             assert ki["problems_per_cta"] == 1, ki       # a latency kernel (4 line-search + 4 speculation warps)
-        if vehicle == "iris" and (mode == dict(group=True) or (mode == dict() and n == B)):
+        if vehicle == "iris" and mode == dict(group=True):
             assert ki["problems_per_cta"] == 32, ki      # the throughput kernel was used
         _eq(u, uo[:n], f"u* {mode}"); _eq(xe, xeo[:n], f"x_evol {mode}")
         _eq(info[:, :7], infoo[:n, :7], f"telemetry {mode}"); _eq(tr, tro[:n], f"trace {mode}")
