@@ -64,32 +64,49 @@ class _DevBuf:
                                          "strides": None}
 
 
+_gather_cache: dict = {}
+
+
 def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
     """One batched solve of this rank's shard followed by the final result gather **device to device**:
     inputs go host -> HBM (pinned staging), the solve kernel runs, every rank's OUT block (x_evol | plan |
-    telemetry) is gathered to rank 0 over NCCL / NVLink straight from the library's device buffer, and rank 0
-    copies the gathered block to the host once.  Returns the dict of [B_total, ...] arrays on rank 0, else None.
+    telemetry) is gathered over NCCL / NVLink straight from the library's device buffer (one all_gather per
+    sub-array, so the gathered arrays are contiguous), and rank 0 copies them once into pinned host memory.
+    Returns the dict of [B_total, ...] arrays on rank 0 (views of reused pinned buffers), else None.
     This is the only collective of the path."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [shard_range(B_total, r, world)[1] - shard_range(B_total, r, world)[0] for r in range(world)]
+    if len(set(sizes)) != 1:
+        raise ValueError("solve_sharded needs equal shards (B_total divisible by the world size)")
     solver.stage(local_problem["x"], u0, info0, xref_win=local_problem.get("xref_win"), rng=local_problem.get("rng"),
                  curr_t=local_problem.get("curr_t"), xdes=local_problem.get("xdes"))
     solver.launch_timed(1, flush_l2=False)          # launch + event wait on the handle's stream
     ptr, nbytes, layout = solver.device_out()
     local = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
-    sizes = [shard_range(B_total, r, world)[1] - shard_range(B_total, r, world)[0] for r in range(world)]
-    if len(set(sizes)) != 1:
-        raise ValueError("solve_sharded needs equal shards (B_total divisible by the world size)")
-    out = torch.empty((world, local.numel()), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, local)            # ~1.5 KB per problem over NVLink
+    key = (world, tuple((k, off, shape) for k, (off, shape) in sorted(layout.items())))
+    if key not in _gather_cache:
+        bufs = {}
+        for k, (off, shape) in layout.items():
+            n = int(np.prod(shape))
+            dev = torch.empty((world, n), dtype=torch.float32, device="cuda")
+            host = torch.empty((world, n), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+            bufs[k] = (dev, host)
+        _gather_cache.clear()
+        _gather_cache[key] = bufs
+    bufs = _gather_cache[key]
+    for k, (off, shape) in layout.items():
+        n = int(np.prod(shape))
+        dist.all_gather_into_tensor(bufs[k][0], local[off // 4: off // 4 + n])   # ~1.5 KB per problem in total
     if rank != 0:
         torch.cuda.current_stream().synchronize()
         return None
-    host = out.cpu().numpy()                           # one D2H of the gathered block
     res = {}
     for k, (off, shape) in layout.items():
-        n = int(np.prod(shape))
-        res[k] = np.concatenate([host[r, off // 4: off // 4 + n].reshape(shape) for r in range(world)], axis=0)
+        bufs[k][1].copy_(bufs[k][0], non_blocking=True)                            # one D2H per array, pinned
+    torch.cuda.current_stream().synchronize()
+    for k, (off, shape) in layout.items():
+        res[k] = bufs[k][1].numpy().reshape((world * shape[0],) + tuple(shape[1:]))
     return res
