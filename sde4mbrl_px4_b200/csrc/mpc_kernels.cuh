@@ -523,6 +523,7 @@ __device__ __forceinline__ float rollout_fwd(const KParams& P, Warp<NU, W>& c, c
 #pragma unroll
         for (int i = 0; i < NU; ++i) up[i] = u[i];
     }
+    if constexpr (MODE != 0) __syncwarp();   // lane 0's last tape writes are visible to every lane that reads the tape next
     return Jp;
 }
 

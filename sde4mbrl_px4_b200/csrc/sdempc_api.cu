@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) 
     tm.ls_bar_id = 1 + team;
 
     mbar_wait(bar, 0);
+    if constexpr (CL) cooperative_groups::this_cluster().sync();   // both CTAs resident before any DSMEM access
 
     const int n = P.H * NU;
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) 
                 for (int i = 0; i < 3; ++i) { const float d = x0[i] - c.xref[16 + i]; e2 = fma_(d, d, e2); }
                 se = se + e2;
                 me = e2 > me ? e2 : me;
+                __syncwarp();   // the window is rebuilt by the next tick
             }
             if (wit == 0 && ls == 0 && lane == 0) {
                 if (P.x_hist != nullptr) {
