@@ -422,3 +422,20 @@ def test_fork_safety_and_node_harness():
             n.close()
     """)
     assert "NODE_OK" in out
+
+
+def test_compute_sanitizer_clean():
+    """memcheck and racecheck (shared-memory hazards, incl. the DSMEM / cluster-barrier kernels) report nothing on
+    tiny solves through every kernel variant (tools/sanitize_probe.py)."""
+    import shutil
+
+    cs = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+    if not os.path.exists(cs):
+        pytest.skip("compute-sanitizer not available")
+    probe = os.path.join(ROOT, "tools", "sanitize_probe.py")
+    for tool, ok_line in (("memcheck", "ERROR SUMMARY: 0 errors"), ("racecheck", "RACECHECK SUMMARY: 0 hazards displayed (0 errors, 0 warnings)")):
+        r = subprocess.run([cs, "--tool", tool, "--print-limit", "5", sys.executable, probe, "cluster", "spec8", "warp", "group",
+                            "pcluster", "team", "closed", "rollout"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+        out = r.stdout + r.stderr
+        assert out.count(" ok {") == 8, out[-3000:]
+        assert ok_line in out, out[-3000:]
