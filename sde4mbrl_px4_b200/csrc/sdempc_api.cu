@@ -550,7 +550,9 @@ static int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(SDEMPC_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
 
-constexpr int GROUP_GP = 4, GROUP_GW = 8;   // problems per warp / warps per CTA of the throughput kernel
+constexpr int GROUP_GW = 8;   // warps per CTA of the throughput kernel
+// problems per warp of the throughput kernel: what fits 227 KB of shared memory next to the staged weights
+constexpr int group_gp(int nu, int w) { return (w == 32 && nu <= 4) ? 4 : (w == 32) ? 3 : 2; }
 constexpr int SPEC_LSW = 4;   // line-search warps of the latency kernel: one per SM sub-partition
 constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0/1/2 accepted, step rejected)
 
@@ -563,7 +565,8 @@ struct KernelChoice {
     void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
     void (*closed_cl)(KParams);
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
-    void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x GROUP_GP problems per CTA (P == 1, W == 32)
+    void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
+    int gp;
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
     bool wreg;
@@ -582,7 +585,8 @@ static KernelChoice make_choice() {
     k.solve_group = nullptr;
     k.solve_pc = nullptr;
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
-    if constexpr (PP == 1 && W == 32) k.solve_group = mpc_group_kernel<NU, W, GROUP_GP, GROUP_GW>;
+    k.gp = group_gp(NU, W);
+    if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
     if constexpr (PP == 1) {
         k.solve_spec = mpc_kernel<NU, W, 1, 1, MODE_SOLVE, SPEC_LSW, SPEC_SGW>;
         k.closed_spec = mpc_kernel<NU, W, 1, 1, MODE_CLOSED_LOOP, SPEC_LSW, SPEC_SGW>;
@@ -743,7 +747,7 @@ static void build_kparams(sdempc_handle* h) {
     g.o_bufA = g.o_bufB = g.o_act3 = g.o_red = g.o_mtape = 0;
     g.ws_stride = align4(q) + 4;
     g.gx_stride = 2 * (6 * W + 8);   // two sets: the network phases process two problems per pass
-    h->smem_bytes_group = ((size_t)kc.wsmem_floats + 4 + (size_t)GROUP_GW * g.gx_stride + (size_t)GROUP_GW * GROUP_GP * g.ws_stride) * 4;
+    h->smem_bytes_group = ((size_t)kc.wsmem_floats + 4 + (size_t)GROUP_GW * g.gx_stride + (size_t)GROUP_GW * kc.gp * g.ws_stride) * 4;
 }
 
 static int ensure_device(sdempc_handle* h) {
@@ -820,13 +824,16 @@ static bool use_pcluster(const sdempc_handle* h, int B) {
 }
 
 static bool use_group(const sdempc_handle* h, int B) {
-    // measured crossover against one warp per problem (tools/batch_sweep.py): ~13 problems per SM
-    return h->kc.solve_group != nullptr && !(h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) && !use_spec(h, B) &&
-           ((h->cfg.flags & SDEMPC_F_GROUP) != 0 || B > 13 * h->sm_count);
+    // measured crossover against one warp per problem (tools/batch_sweep.py): ~13 problems per SM with 4 problems
+    // per warp (iris), ~10 with 2 (width 64); with 3 (nu = 6, width 32) it never wins at these sizes: flag only
+    if (h->kc.solve_group == nullptr || (h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) || use_spec(h, B)) return false;
+    if (h->cfg.flags & SDEMPC_F_GROUP) return true;
+    const int per_sm = h->kc.gp == 4 ? 13 : h->kc.gp == 2 ? 10 : (1 << 20);
+    return B > per_sm * h->sm_count;
 }
 
 static int ensure_mtape_group(sdempc_handle* h, int grid) {
-    const size_t tapes = (size_t)grid * GROUP_GW * GROUP_GP;
+    const size_t tapes = (size_t)grid * GROUP_GW * h->kc.gp;
     if (tapes <= h->mtape_group_n) return 0;
     if (h->d_mtape_group) cudaFree(h->d_mtape_group);
     h->d_mtape_group = nullptr;
@@ -1299,7 +1306,7 @@ int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
     out[0] = (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
-    out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * GROUP_GP : h->kc.G;
+    out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * h->kc.gp : h->kc.G;
     out[3] = h->regs;
     out[4] = h->last_grid;
     out[5] = h->sm_count;

@@ -148,8 +148,7 @@ def test_three_kernels_agree(solver, O, vehicle, width):
     # (flags, batch, expected threads per CTA; 255 = 8-warp latency kernel, 128 = 2-CTA cluster latency kernel)
     modes = [(dict(speculative_ls=True), B, 255), (dict(sequential_ls=True), B, 256), (dict(), 9, 128),
              (dict(no_cluster=True), 9, 255), (dict(), B, 256)]
-    if w32:
-        modes.append((dict(group=True), 7, 256))
+    modes.append((dict(group=True), 7, 256))
     for mode, n, threads in modes:
         cfg, s, _ = _pair(solver, O, vehicle, "traj", **ov, **mode)
         u, xe, info, tr = s.solve(pr["x"][:n], u0[:n], i0[:n], xref_win=pr["xref_win"][:n], rng=pr["rng"][:n], want_trace=True)
@@ -157,8 +156,8 @@ def test_three_kernels_agree(solver, O, vehicle, width):
         assert ki["threads_per_cta"] == (256 if threads == 255 else threads), (mode, ki)
         if threads in (255, 128):
             assert ki["problems_per_cta"] == 1, ki       # a latency kernel (4 line-search + 4 speculation warps)
-        if vehicle == "iris" and mode == dict(group=True):
-            assert ki["problems_per_cta"] == 32, ki      # the throughput kernel was used
+        if mode == dict(group=True):   # the throughput kernel was used: 8 warps x (4 | 3 | 2) problems
+            assert ki["problems_per_cta"] == {("iris", None): 32, ("hexa", None): 16, ("hexa", 32): 24}[(vehicle, width)], ki
         _eq(u, uo[:n], f"u* {mode}"); _eq(xe, xeo[:n], f"x_evol {mode}")
         _eq(info[:, :7], infoo[:n, :7], f"telemetry {mode}"); _eq(tr, tro[:n], f"trace {mode}")
 

@@ -5,9 +5,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sde4mbrl_px4_b200 import config, model_io, solver, synthetic
-cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
-blob = model_io.synthetic_model("iris").to_blob()
-for B in (150, 296, 592, 1184, 1776, 2368, 3552, 4096, 8192):
+vehicle = sys.argv[1] if len(sys.argv) > 1 else "iris"
+width = int(sys.argv[2]) if len(sys.argv) > 2 else None
+cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{vehicle}_traj.yaml"))
+blob = model_io.synthetic_model(vehicle, width=width).to_blob()
+for B in ((150, 296, 592, 1184, 1776, 2368, 3552, 4096, 8192) if vehicle == "iris" else (592, 1184, 2368, 4096)):
     row = []
     for mode in ("sequential_ls", "group", "speculative_ls"):
         if mode == "speculative_ls" and B > 592:
