@@ -65,6 +65,24 @@ def test_host_only_calls_and_argument_errors(built):
         solver.MPCSolver(cfg, bytes(bad))
 
 
+def test_empty_and_malformed_batches_are_rejected(built):
+    """Argument errors are reported before any CUDA call (so this runs without a GPU)."""
+    cfg, blob, _ = make_setup("iris", "traj")
+    s = solver.MPCSolver(cfg, blob)
+    e = np.zeros((0, 13), np.float32)
+    with pytest.raises(RuntimeError, match="B must be >= 1"):
+        s.solve(e, np.zeros((0, 20, 4), np.float32), np.zeros((0, 8), np.float32), xdes=e, rng=np.zeros((0, 2), np.uint64))
+    x = np.zeros((2, 13), np.float32)
+    x[:, 6] = 1
+    u, info = s.reset(2)
+    with pytest.raises(RuntimeError, match="one of xref_win, curr_t, xdes"):
+        s.solve(x, u, info, rng=np.zeros((2, 2), np.uint64))
+    with pytest.raises(RuntimeError, match="set_trajectory"):
+        s.solve(x, u, info, curr_t=np.zeros(2, np.float32), rng=np.zeros((2, 2), np.uint64))
+    with pytest.raises(RuntimeError, match="rng is required"):
+        s.solve(x, u, info, xdes=x)
+
+
 def test_compute_fails_loudly_without_gpu(built):
     """There is no CPU fallback: on a box without CUDA the solve raises instead of computing."""
     import torch
