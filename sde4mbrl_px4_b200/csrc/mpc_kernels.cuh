@@ -49,6 +49,7 @@ struct KParams {
     const float* traj;   // [T][14] internal frame, or nullptr
     int T;
     float2* mtape_g;     // global MLP tape scratch (W = 64), per resident warp
+    float* stape_g;      // quad kernel: global step tape, [slot][H][20]
     // per-warp shared-memory layout (float offsets), computed on the host
     int ws_stride, o_xk, o_yk, o_g, o_xp, o_uprev, o_xref, o_xi, o_xtape, o_stape, o_mtape, o_bufA, o_bufB,
         o_act3, o_lz, o_red, o_zb, o_lob, o_g2;
