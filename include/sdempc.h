@@ -59,8 +59,6 @@ extern "C" {
 #define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
 #define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
 #define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a 2-CTA cluster */
-#define SDEMPC_F_QUAD 64u          /* throughput kernel with 4 lanes per problem (8 problems per warp, width 32, P = 1) */
-#define SDEMPC_F_QUAD8 128u        /* same with 8 lanes per problem (4 problems per warp) */
 /* Default kernel choice: latency kernels when the batch fits one problem per SM (or per cluster), the throughput
  * kernel for large batches (> ~13 problems per SM; P = 1, width 32), one warp per (problem, particle) otherwise.
  * All of them produce bit-identical results. */

@@ -81,8 +81,6 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
         flags |= _abi.F_GROUP
     if overrides.get("no_cluster", False):
         flags |= _abi.F_NO_CLUSTER
-    if overrides.get("quad", False):
-        flags |= _abi.F_QUAD8 if int(overrides["quad"]) == 8 else _abi.F_QUAD
     c.flags = flags
     for t, v in enumerate(time_steps(cfg)):
         c.dt[t] = float(v)

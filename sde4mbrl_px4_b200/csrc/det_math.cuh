@@ -175,6 +175,17 @@ __device__ __forceinline__ void det_softplus_sigmoid(float s, float& sp, float& 
     sg = s >= 0.0f ? r : __fmul_rn(e, r);
 }
 
+// same sequences; the sigmoid is skipped when not wanted (sg = 0)
+__device__ __forceinline__ void det_softplus_sigmoid_opt(float s, float& sp, float& sg, bool want_sg) {
+    float e = det_exp_nonpos(-fabsf(s));
+    sp = __fadd_rn(s > 0.0f ? s : 0.0f, det_log1p01(e));
+    sg = 0.f;
+    if (want_sg) {
+        float r = det_recip12(__fadd_rn(1.0f, e));
+        sg = s >= 0.0f ? r : __fmul_rn(e, r);
+    }
+}
+
 __device__ __forceinline__ float det_log(float u) {
     uint32_t b = __float_as_uint(u);
     int ex = (int)((b >> 23) & 0xffu) - 127;

@@ -49,7 +49,6 @@ struct KParams {
     const float* traj;   // [T][14] internal frame, or nullptr
     int T;
     float2* mtape_g;     // global MLP tape scratch (W = 64), per resident warp
-    float* stape_g;      // quad kernel: global step tape, [slot][H][20]
     // per-warp shared-memory layout (float offsets), computed on the host
     int ws_stride, o_xk, o_yk, o_g, o_xp, o_uprev, o_xref, o_xi, o_xtape, o_stape, o_mtape, o_bufA, o_bufB,
         o_act3, o_lz, o_red, o_zb, o_lob, o_g2;
@@ -364,10 +363,7 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
         for (int k = 0; k < NIN; ++k) {
             const float2 wv = c.W1P(uu, k);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                a[p][k & 3].x = fma_(wv.x, z[p][k], a[p][k & 3].x);
-                a[p][k & 3].y = fma_(wv.y, z[p][k], a[p][k & 3].y);
-            }
+            for (int p = 0; p < NP; ++p) a[p][k & 3] = fma2_(wv, splat(z[p][k]), a[p][k & 3]);
         }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
@@ -413,7 +409,35 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
     }
     __syncwarp();
     // ---- output layer: lanes 0..5 drift rows, 6..11 diffusion rows ----
-    {
+    if constexpr (NP == 2) {
+        // lanes 0..11 serve problem 0, lanes 12..23 problem 1 (24..31 shadow lane 23): one pass of weight-row
+        // loads and half the activation loads of the sequential form
+        const int l24 = lane < 24 ? lane : 23;
+        const int p = l24 >= 12 ? 1 : 0;
+        const int o = l24 - 12 * p;
+        const float* row = c.ws + L::W3R + o * L::W3R_STRIDE;
+        const float* act = c.act3 + p * xstride + (o >= 6 ? W + 4 : 0);
+        float2 aA = make_float2(c.ws[L::B3 + o], 0.f), aB = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < W; k += 4) {
+            const float4 wv = lds4(row + k);
+            const float4 hv = lds4(act + k);
+            aA = fma2_(xy(wv), xy(hv), aA);
+            aB = fma2_(zw(wv), zw(hv), aB);
+        }
+        const float out = (aA.x + aA.y) + (aB.x + aB.y);
+        const float s0 = P.sig0[o >= 6 ? o - 6 : 0];
+        float sp, sg;
+        det_softplus_sigmoid_opt(out, sp, sg, tape);
+        float* obp = p ? ob[1] : ob[0];
+        if (lane < 24) {
+            if (o < 6) obp[o] = out;
+            else {
+                obp[o] = s0 * sp;
+                if (tape) obp[o + 6] = s0 * sg;
+            }
+        }
+    } else {
         const int o = lane < 12 ? lane : 11;
         const float* row = c.ws + L::W3R + o * L::W3R_STRIDE;
         // the four partial sums of SPEC-ARITH packed two per FFMA2: (a0, a1) and (a2, a3)
@@ -431,26 +455,15 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
             }
         }
         const float s0 = P.sig0[o >= 6 ? o - 6 : 0];
-        if constexpr (NP == 2) {   // the two problems' softplus / sigmoid packed into FFMA2
-            const float2 out = make_float2((aA[0].x + aA[0].y) + (aB[0].x + aB[0].y), (aA[1].x + aA[1].y) + (aB[1].x + aB[1].y));
-            float2 sp, sg;
-            det_softplus_sigmoid2(out, sp, sg, tape);
-            if (lane < 6) { ob[0][lane] = out.x; ob[1][lane] = out.y; }
-            else if (lane < 12) {
-                ob[0][lane] = s0 * sp.x; ob[1][lane] = s0 * sp.y;
-                if (tape) { ob[0][lane + 6] = s0 * sg.x; ob[1][lane + 6] = s0 * sg.y; }
-            }
-        } else {
 #pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                const float out = (aA[p].x + aA[p].y) + (aB[p].x + aB[p].y);
-                float sp, sg;
-                det_softplus_sigmoid(out, sp, sg);
-                if (lane < 6) ob[p][lane] = out;
-                else if (lane < 12) {
-                    ob[p][lane] = s0 * sp;
-                    if (tape) ob[p][lane + 6] = s0 * sg;
-                }
+        for (int p = 0; p < NP; ++p) {
+            const float out = (aA[p].x + aA[p].y) + (aB[p].x + aB[p].y);
+            float sp, sg;
+            det_softplus_sigmoid(out, sp, sg);
+            if (lane < 6) ob[p][lane] = out;
+            else if (lane < 12) {
+                ob[p][lane] = s0 * sp;
+                if (tape) ob[p][lane + 6] = s0 * sg;
             }
         }
     }

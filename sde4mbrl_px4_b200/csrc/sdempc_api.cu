@@ -20,7 +20,6 @@
 #include "mpc_group.cuh"
 #include "mpc_kernels.cuh"
 #include "mpc_pcluster.cuh"
-#include "mpc_quad.cuh"
 
 using namespace sdempc;
 
@@ -532,108 +531,6 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
     }
 }
 
-// Throughput kernel, LPP lanes per problem (mpc_quad.cuh): QW warps per CTA, 32 / LPP problems per warp.  P = 1.
-template <int NU, int W, int LPP, int QW>
-__global__ void __launch_bounds__(QW * 32, 1) mpc_quad_kernel(const __grid_constant__ KParams P) {
-    using L = QLayout<NU, W, LPP>;
-    constexpr int QP = 32 / LPP;
-    extern __shared__ __align__(128) float smem[];
-    float* ws = smem;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::TOTAL);
-    float* regions = smem + L::TOTAL + 4;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    stage_weights<L::TOTAL * 4>(ws, P.wimg, bar);
-
-    Quad<NU, W, LPP> c;
-    c.lane = lane; c.q = lane / LPP; c.r = lane % LPP;
-    c.wr = ws + 4 * c.r;
-    float* wbase = regions + (size_t)warp * QP * P.ws_stride;
-    c.reg = wbase + (size_t)c.q * P.ws_stride;
-    {
-        const size_t slot = ((size_t)blockIdx.x * QW + warp) * QP + c.q;
-        c.mt = reinterpret_cast<float*>(P.mtape_g) + slot * (size_t)P.H * 4 * W + 4 * c.r;
-        c.st = P.stape_g + slot * (size_t)P.H * 20;
-    }
-
-    mbar_wait(bar, 0);
-
-    const int n = P.H * NU;
-    const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
-    // balanced assignment: every round spreads up to (#warps x QP) problems evenly over all warps of the grid
-    const int nwarps = gridDim.x * QW, wid = blockIdx.x * QW + warp;
-    for (int r0 = 0; r0 < P.B; r0 += nwarps * QP) {
-        const int Br = (P.B - r0) < nwarps * QP ? (P.B - r0) : nwarps * QP;
-        const int lo = (int)(((long long)wid * Br) / nwarps), hi = (int)(((long long)(wid + 1) * Br) / nwarps);
-        const int b0 = r0 + lo;
-        const int nprob = hi - lo;
-        if (nprob <= 0) continue;
-        for (int q = 0; q < nprob; ++q) {
-            const int b = b0 + q;
-            float* rb = wbase + (size_t)q * P.ws_stride;
-            build_window(P, lane, rb + P.o_xref, P.xref_win ? P.xref_win + (size_t)b * (P.H + 1) * NX : nullptr,
-                         P.curr_t ? P.curr_t + b : nullptr, P.xdes ? P.xdes + (size_t)b * NX : nullptr, 0.f, false);
-            if (P.xi_override != nullptr) {
-                if (lane < P.H) {
-                    const float* src = P.xi_override + ((size_t)b * P.H + lane) * 6;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) rb[P.o_xi + lane * 8 + i] = __ldg(src + i);
-                }
-            } else {
-                gen_noise(lane, P.rng[2 * (size_t)b], P.rng[2 * (size_t)b + 1], 0u, 0u, P.H, rb + P.o_xi);
-            }
-            const float* pin = P.u_plan + (size_t)b * n;
-            if (lane < NU) rb[P.o_uprev + lane] = __ldg(pin + lane);
-            for (int i = lane; i < n; i += 32) {
-                const int t = i / NU, ii = i % NU;
-                const int ts = (P.flags & SDEMPC_F_NO_SHIFT) ? t : (t + 1 < P.H ? t + 1 : P.H - 1);
-                rb[P.o_xk + i] = clipf(__ldg(pin + ts * NU + ii), P.u_lo[ii], P.u_hi[ii]);
-            }
-        }
-        // the LPP lanes of slot q carry problem b0 + q; empty slots shadow problem b0 and store nothing
-        const bool mine = c.q < nprob;
-        const int bq = b0 + (mine ? c.q : 0);
-        {
-            float tmp[NX], x0[NX];
-#pragma unroll
-            for (int i = 0; i < NX; ++i) tmp[i] = __ldg(P.x + (size_t)bq * NX + i);
-            if (enu) enu_ned(tmp, x0);
-            else {
-#pragma unroll
-                for (int i = 0; i < NX; ++i) x0[i] = tmp[i];
-            }
-            if (c.r == 0) store13(c.reg + P.o_xtape, x0);
-        }
-        float s = P.info[bq].stepsize;
-        s = s > 0.f ? s : P.init_step;
-        __syncwarp();
-        sdempc_info inf;
-        q_apg_solve<NU, W, LPP>(P, c, s, mine, inf,
-                                (P.trace != nullptr && mine) ? P.trace + (size_t)bq * P.max_iter * SDEMPC_TRACE_W : nullptr);
-        if (mine && c.r == 0) P.info_out[bq] = inf;
-        for (int q = 0; q < nprob; ++q) {
-            const int b = b0 + q;
-            const float* rb = wbase + (size_t)q * P.ws_stride;
-            for (int i = lane; i < n; i += 32) P.u_plan_out[(size_t)b * n + i] = rb[P.o_xk + i];
-            if (lane <= P.H) {
-                float row[NX], o[NX];
-#pragma unroll
-                for (int i = 0; i < NX; ++i) row[i] = rb[P.o_xtape + lane * 16 + i] * 1.0f;   // mean over P = 1 particle
-                quat_renorm(row + 6);
-                if (enu) enu_ned(row, o);
-                else {
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) o[i] = row[i];
-                }
-                float* dst = P.x_evol + (size_t)b * (P.H + 1) * NX + lane * NX;
-#pragma unroll
-                for (int i = 0; i < NX; ++i) dst[i] = o[i];
-            }
-        }
-        __syncwarp();
-    }
-}
-
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -656,9 +553,6 @@ static int fail(int code, const char* fmt, ...) {
 constexpr int GROUP_GW = 8;   // warps per CTA of the throughput kernel
 // problems per warp of the throughput kernel: what fits 227 KB of shared memory next to the staged weights
 constexpr int group_gp(int nu, int w) { return (w == 32 && nu <= 4) ? 4 : (w == 32) ? 3 : 2; }
-// quad kernel variants: lanes per problem / warps per CTA (32 problems per CTA when width 32)
-constexpr int QUAD_LPP_A = 4, QUAD_QW_A = 4;
-constexpr int QUAD_LPP_B = 8, QUAD_QW_B = 8;
 constexpr int SPEC_LSW = 4;   // line-search warps of the latency kernel: one per SM sub-partition
 constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0/1/2 accepted, step rejected)
 
@@ -672,8 +566,6 @@ struct KernelChoice {
     void (*closed_cl)(KParams);
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
-    void (*solve_quad[2])(KParams);   // throughput mode, 4 / 8 lanes per problem (P == 1, width 32)
-    int quad_floats[2];
     int gp;
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
@@ -692,14 +584,6 @@ static KernelChoice make_choice() {
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     k.solve_pc = nullptr;
-    k.solve_quad[0] = k.solve_quad[1] = nullptr;
-    k.quad_floats[0] = k.quad_floats[1] = 0;
-    if constexpr (PP == 1 && W == 32) {
-        k.solve_quad[0] = mpc_quad_kernel<NU, W, QUAD_LPP_A, QUAD_QW_A>;
-        k.solve_quad[1] = mpc_quad_kernel<NU, W, QUAD_LPP_B, QUAD_QW_B>;
-        k.quad_floats[0] = QLayout<NU, W, QUAD_LPP_A>::TOTAL;
-        k.quad_floats[1] = QLayout<NU, W, QUAD_LPP_B>::TOTAL;
-    }
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
     k.gp = group_gp(NU, W);
     if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
@@ -736,13 +620,6 @@ struct sdempc_handle {
     KParams kp;                       // template (config + model + layout)
     KParams kp_group;                 // same with the per-problem layout of the group kernel
     size_t smem_bytes_group = 0;
-    KParams kp_quad;                  // per-problem layout of the quad kernel
-    size_t smem_bytes_quad[2] = {0, 0};
-    std::vector<float> wimg_quad[2];
-    float* d_wimg_quad[2] = {nullptr, nullptr};
-    float* d_mtape_quad = nullptr; float* d_stape_quad = nullptr;
-    size_t tape_quad_slots = 0;
-    int staged_quad = -1;             // -1: not the quad kernel, else the variant index
     size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
     bool dev_ready = false;
@@ -804,52 +681,6 @@ static void pack_weights(sdempc_handle* h) {
             I[B2 + 2 * j + n] = b2[n][j];
         }
     }
-}
-
-// Role-interleaved image of the quad kernel (QLayout in mpc_quad.cuh; the offsets below mirror it).
-static void pack_weights_quad(sdempc_handle* h, int variant, int LPP) {
-    const int NU = h->mh.nu, W = h->mh.width, NIN = 6 + NU;
-    const int UPQ = W / LPP, OO = (6 + LPP - 1) / LPP, II = (NIN + LPP - 1) / LPP, CH = 4 * LPP;
-    const int oW1 = 0, oB1 = oW1 + UPQ * (NIN / 2) * CH, oW2 = oB1 + (UPQ / 2) * CH, oB2 = oW2 + UPQ * (W / 2) * CH,
-              oW3 = oB2 + (UPQ / 2) * CH, oB3 = oW3 + OO * (W / 2) * CH, oW3C = oB3 + OO * CH, oW2T = oW3C + UPQ * 3 * CH,
-              oW1T = oW2T + UPQ * (W / 2) * CH, TOTAL = oW1T + II * (W / 2) * CH;
-    std::vector<float>& I = h->wimg_quad[variant];
-    I.assign(TOTAL, 0.f);
-    const float* p = h->weights.data();
-    const float *W1[2], *b1[2], *W2[2], *b2[2], *W3[2], *b3[2];
-    for (int n = 0; n < 2; ++n) {
-        W1[n] = p; p += (size_t)W * NIN;
-        b1[n] = p; p += W;
-        W2[n] = p; p += (size_t)W * W;
-        b2[n] = p; p += W;
-        W3[n] = p; p += 6 * (size_t)W;
-        b3[n] = p; p += 6;
-    }
-    for (int r = 0; r < LPP; ++r)
-        for (int n = 0; n < 2; ++n) {
-            for (int jj = 0; jj < UPQ; ++jj) {
-                const int j = UPQ * r + jj;
-                for (int k = 0; k < NIN; ++k) I[oW1 + (jj * (NIN / 2) + k / 2) * CH + 4 * r + 2 * (k & 1) + n] = W1[n][j * NIN + k];
-                for (int k = 0; k < W; ++k) {
-                    I[oW2 + (jj * (W / 2) + k / 2) * CH + 4 * r + 2 * (k & 1) + n] = W2[n][j * W + k];
-                    I[oW2T + (jj * (W / 2) + k / 2) * CH + 4 * r + 2 * (k & 1) + n] = W2[n][k * W + j];   // row j of W2^T
-                }
-                for (int o = 0; o < 6; ++o) I[oW3C + (jj * 3 + o / 2) * CH + 4 * r + 2 * (o & 1) + n] = W3[n][o * W + j];
-                I[oB1 + (jj / 2) * CH + 4 * r + 2 * (jj & 1) + n] = b1[n][j];
-                I[oB2 + (jj / 2) * CH + 4 * r + 2 * (jj & 1) + n] = b2[n][j];
-            }
-            for (int oo = 0; oo < OO; ++oo) {
-                const int o = oo * LPP + r;
-                if (o >= 6) continue;
-                for (int k = 0; k < W; ++k) I[oW3 + (oo * (W / 2) + k / 2) * CH + 4 * r + 2 * (k & 1) + n] = W3[n][o * W + k];
-                I[oB3 + oo * CH + 4 * r + n] = b3[n][o];
-            }
-            for (int ii = 0; ii < II; ++ii) {
-                const int i = ii * LPP + r;
-                if (i >= NIN) continue;
-                for (int j = 0; j < W; ++j) I[oW1T + (ii * (W / 2) + j / 2) * CH + 4 * r + 2 * (j & 1) + n] = W1[n][j * NIN + i];
-            }
-        }
 }
 
 static int align4(int v) { return (v + 3) & ~3; }
@@ -917,25 +748,6 @@ static void build_kparams(sdempc_handle* h) {
     g.ws_stride = align4(q) + 4;
     g.gx_stride = 2 * (6 * W + 8);   // two sets: the network phases process two problems per pass
     h->smem_bytes_group = ((size_t)kc.wsmem_floats + 4 + (size_t)GROUP_GW * g.gx_stride + (size_t)GROUP_GW * kc.gp * g.ws_stride) * 4;
-    // quad kernel: problem data + two 2W-float exchange buffers per problem; both tapes in global memory.
-    // The region stride is 4 mod 32 floats: the problems of a warp hit distinct bank groups with LDS.128.
-    KParams& u = h->kp_quad;
-    u = k;
-    int z = 0;
-    u.o_xk = z; z += n; u.o_yk = z; z += n; u.o_g = z; z += n; u.o_xp = z; z += n;
-    u.o_uprev = z; z += 8;
-    u.o_xref = z; z += (H + 1) * 16;
-    u.o_xi = z; z += H * 8;
-    u.o_xtape = z; z += (H + 1) * 16;
-    u.o_bufA = z; z += 2 * W; u.o_bufB = z; z += 2 * W;
-    u.o_lz = z; z += 24;
-    u.o_stape = u.o_act3 = u.o_red = u.o_mtape = u.o_lob = u.o_zb = 0;
-    z = align4(z);
-    while (z % 32 != 4) z += 4;
-    u.ws_stride = z;
-    const int qlpp[2] = {QUAD_LPP_A, QUAD_LPP_B}, qqw[2] = {QUAD_QW_A, QUAD_QW_B};
-    for (int v = 0; v < 2; ++v)
-        h->smem_bytes_quad[v] = kc.solve_quad[v] ? ((size_t)kc.quad_floats[v] + 4 + (size_t)qqw[v] * (32 / qlpp[v]) * u.ws_stride) * 4 : 0;
 }
 
 static int ensure_device(sdempc_handle* h) {
@@ -981,13 +793,6 @@ static int ensure_device(sdempc_handle* h) {
         if (h->smem_bytes_group > (size_t)prop.sharedMemPerBlockOptin) h->kc.solve_group = nullptr;   // does not fit: use one warp per problem
         else CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_group));
     }
-    for (int v = 0; v < 2; ++v) {
-        if (!h->kc.solve_quad[v]) continue;
-        if (h->smem_bytes_quad[v] > (size_t)prop.sharedMemPerBlockOptin) { h->kc.solve_quad[v] = nullptr; continue; }
-        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_quad[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_quad[v]));
-        CUDA_TRY(cudaMalloc(&h->d_wimg_quad[v], h->wimg_quad[v].size() * 4));
-        CUDA_TRY(cudaMemcpy(h->d_wimg_quad[v], h->wimg_quad[v].data(), h->wimg_quad[v].size() * 4, cudaMemcpyHostToDevice));
-    }
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, h->kc.solve));
     h->regs = fa.numRegs;
@@ -1003,7 +808,7 @@ static bool use_spec(const sdempc_handle* h, int B) {
     // latency regime: at most one problem per SM, or forced by the flag; bit-identical to the batched kernel
     if (h->kc.solve_spec == nullptr || h->cfg.maxls < 1 || (h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS)) return false;
     if (h->cfg.flags & SDEMPC_F_SPECULATIVE_LS) return true;
-    return !(h->cfg.flags & (SDEMPC_F_GROUP | SDEMPC_F_QUAD | SDEMPC_F_QUAD8)) && B <= h->sm_count;
+    return !(h->cfg.flags & SDEMPC_F_GROUP) && B <= h->sm_count;
 }
 
 // cluster variant of the latency kernel: two SMs per problem
@@ -1027,33 +832,10 @@ static bool use_group(const sdempc_handle* h, int B) {
     return B > per_sm * h->sm_count;
 }
 
-// quad kernel variant to use for a batch of B, or -1
-static int use_quad(const sdempc_handle* h, int B) {
-    if ((h->cfg.flags & SDEMPC_F_SEQUENTIAL_LS) || use_spec(h, B)) return -1;
-    if ((h->cfg.flags & SDEMPC_F_QUAD8) && h->kc.solve_quad[1]) return 1;
-    if ((h->cfg.flags & SDEMPC_F_QUAD) && h->kc.solve_quad[0]) return 0;
-    return -1;
-}
-
-static int ensure_tape_quad(sdempc_handle* h, int grid, int variant) {
-    const int qlpp[2] = {QUAD_LPP_A, QUAD_LPP_B}, qqw[2] = {QUAD_QW_A, QUAD_QW_B};
-    const size_t slots = (size_t)grid * qqw[variant] * (32 / qlpp[variant]);
-    if (slots <= h->tape_quad_slots) return 0;
-    if (h->d_mtape_quad) cudaFree(h->d_mtape_quad);
-    if (h->d_stape_quad) cudaFree(h->d_stape_quad);
-    h->d_mtape_quad = h->d_stape_quad = nullptr;
-    h->tape_quad_slots = 0;
-    CUDA_TRY(cudaMalloc(&h->d_mtape_quad, slots * (size_t)h->cfg.horizon * 4 * h->mh.width * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&h->d_stape_quad, slots * (size_t)h->cfg.horizon * 20 * sizeof(float)));
-    h->tape_quad_slots = slots;
-    return 0;
-}
-
 static int ensure_mtape_group(sdempc_handle* h, int grid) {
     const size_t tapes = (size_t)grid * GROUP_GW * h->kc.gp;
     if (tapes <= h->mtape_group_n) return 0;
-    if (h->d_mtape_group) cudaFree(h->d_mtape_group); cudaFree(h->d_mtape_quad); cudaFree(h->d_stape_quad);
-        cudaFree(h->d_wimg_quad[0]); cudaFree(h->d_wimg_quad[1]);
+    if (h->d_mtape_group) cudaFree(h->d_mtape_group);
     h->d_mtape_group = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_mtape_group, tapes * (size_t)h->cfg.horizon * 2 * h->mh.width * sizeof(float2)));
     h->mtape_group_n = tapes;
@@ -1140,16 +922,12 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     else in_bytes += a16((size_t)B * 16);
     const size_t out_bytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * sizeof(sdempc_info)) + 64;
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
-    const int quad = use_quad(h, B);
-    const bool spec = use_spec(h, B), group = quad < 0 && use_group(h, B);
+    const bool spec = use_spec(h, B), group = use_group(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
     const bool cl = use_cluster(h, B), pcl = use_pcluster(h, B);
-    const int quad_ppc = quad == 0 ? QUAD_QW_A * (32 / QUAD_LPP_A) : QUAD_QW_B * (32 / QUAD_LPP_B);   // problems per CTA
-    const int grid = quad >= 0 ? std::max(1, std::min((2 * B + quad_ppc - 1) / quad_ppc, h->sm_count))
-                          : pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
+    const int grid = pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
-    if (quad >= 0) { if ((rc = ensure_tape_quad(h, grid, quad))) return rc; }
-    else if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
+    if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
     else if ((rc = ensure_mtape(h, grid))) return rc;
     if (a->trace) {
         const size_t tb = (size_t)B * h->cfg.max_iter * SDEMPC_TRACE_W * 4;
@@ -1161,7 +939,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
         }
         CUDA_TRY(cudaMemsetAsync(h->d_trace, 0, tb, h->stream));
     }
-    KParams k = quad >= 0 ? h->kp_quad : group ? h->kp_group : h->kp;
+    KParams k = group ? h->kp_group : h->kp;
     Packer pk{h->h_in, h->d_in};
     k.B = B;
     k.x = pk.put(a->x, (size_t)B * NX);
@@ -1179,12 +957,6 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
-    if (quad >= 0) {
-        k.wimg = h->d_wimg_quad[quad];
-        k.mtape_g = reinterpret_cast<float2*>(h->d_mtape_quad);
-        k.stape_g = h->d_stape_quad;
-    }
-    h->staged_quad = quad;
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl;
     return 0;
 }
@@ -1206,14 +978,6 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
         h->launches += 1;
         return 0;
     }
-    for (int v = 0; v < 2; ++v)
-        if (fn != nullptr && fn == h->kc.solve_quad[v]) {
-            const int threads = (v == 0 ? QUAD_QW_A : QUAD_QW_B) * 32;
-            void* args[] = {const_cast<KParams*>(&k)};
-            CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, h->smem_bytes_quad[v], h->stream));
-            h->launches += 1;
-            return 0;
-        }
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
     const int threads = spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
@@ -1222,11 +986,6 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
     CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, smem, h->stream));
     h->launches += 1;
     return 0;
-}
-
-static void (*staged_fn(const sdempc_handle* h))(KParams) {
-    return h->staged_quad >= 0 ? h->kc.solve_quad[h->staged_quad] : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl
-           : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
 static int fetch_solve(sdempc_handle* h, const sdempc_solve_args* a) {
@@ -1275,8 +1034,6 @@ int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbyte
     h->weights.resize(2 * per_net);
     memcpy(h->weights.data(), (const char*)model_blob + sizeof mh, 2 * per_net * 4);
     pack_weights(h);
-    if (h->kc.solve_quad[0]) pack_weights_quad(h, 0, QUAD_LPP_A);
-    if (h->kc.solve_quad[1]) pack_weights_quad(h, 1, QUAD_LPP_B);
     build_kparams(h);
     *out = h;
     return 0;
@@ -1391,7 +1148,7 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     for (int i = 0; i < n; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch(h, staged_fn(h), h->staged, h->last_grid);
+        int rc = launch(h, h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -1432,7 +1189,7 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     int rc = stage_solve(h, a);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, staged_fn(h), h->staged, h->last_grid))) return rc;
+    if ((rc = launch(h, h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
     float t = 0.f;
@@ -1551,14 +1308,6 @@ int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
     out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * h->kc.gp : h->kc.G;
     out[3] = h->regs;
-    if (h->staged_quad >= 0) {
-        const int v = h->staged_quad;
-        out[0] = (v == 0 ? QUAD_QW_A : QUAD_QW_B) * 32;
-        out[1] = (int32_t)h->smem_bytes_quad[v];
-        out[2] = v == 0 ? QUAD_QW_A * (32 / QUAD_LPP_A) : QUAD_QW_B * (32 / QUAD_LPP_B);
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, h->kc.solve_quad[v]) == cudaSuccess) out[3] = fa.numRegs;
-    }
     out[4] = h->last_grid;
     out[5] = h->sm_count;
     return 0;

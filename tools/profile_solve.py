@@ -16,10 +16,9 @@ ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--vehicle", default="iris")
 ap.add_argument("--particles", type=int, default=1)
 ap.add_argument("--launches", type=int, default=1)
-ap.add_argument("--quad", type=int, default=0, help="4 or 8: quad kernel variant")
 a = ap.parse_args()
 cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{a.vehicle}_traj.yaml"))
-cfg = config.build_config(cfgd, max_iter=a.iters, rtol=0.0, atol=0.0, num_particles=a.particles, quad=a.quad)
+cfg = config.build_config(cfgd, max_iter=a.iters, rtol=0.0, atol=0.0, num_particles=a.particles)
 blob = model_io.synthetic_model(a.vehicle).to_blob()
 pr = synthetic.batched_problems(a.batch, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=0)
 s = solver.MPCSolver(cfg, blob)
