@@ -108,6 +108,14 @@ struct Layout {
     static constexpr int SMEM_FLOATS = WREG ? PART_A : TOTAL;
 };
 
+#ifndef SDEMPC_L3_OFF
+#define SDEMPC_L3_OFF 16
+#endif
+#ifndef SDEMPC_LZ_OFF
+#define SDEMPC_LZ_OFF 16
+#endif
+constexpr int L3_OFF = SDEMPC_L3_OFF, LZ_OFF = SDEMPC_LZ_OFF;   // first lane of the second problem in the split layers
+
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ float2 xy(float4 v) { return make_float2(v.x, v.y); }
@@ -363,7 +371,14 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
         for (int k = 0; k < NIN; ++k) {
             const float2 wv = c.W1P(uu, k);
 #pragma unroll
-            for (int p = 0; p < NP; ++p) a[p][k & 3] = fma2_(wv, splat(z[p][k]), a[p][k & 3]);
+            for (int p = 0; p < NP; ++p) {
+                if constexpr (NP == 1) {   // latency path: two scalar chains are a little shorter than one packed chain
+                    a[p][k & 3].x = fma_(wv.x, z[p][k], a[p][k & 3].x);
+                    a[p][k & 3].y = fma_(wv.y, z[p][k], a[p][k & 3].y);
+                } else {
+                    a[p][k & 3] = fma2_(wv, splat(z[p][k]), a[p][k & 3]);
+                }
+            }
         }
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
@@ -410,11 +425,12 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
     __syncwarp();
     // ---- output layer: lanes 0..5 drift rows, 6..11 diffusion rows ----
     if constexpr (NP == 2) {
-        // lanes 0..11 serve problem 0, lanes 12..23 problem 1 (24..31 shadow lane 23): one pass of weight-row
-        // loads and half the activation loads of the sequential form
-        const int l24 = lane < 24 ? lane : 23;
-        const int p = l24 >= 12 ? 1 : 0;
-        const int o = l24 - 12 * p;
+        // lanes 0..11 serve problem 0, lanes 16..27 problem 1 (the others shadow row 11): one pass of weight-row
+        // loads and half the activation loads of the sequential form; each quarter warp reads rows whose
+        // 16-byte chunks fall in distinct banks
+        const int p = lane >= L3_OFF ? 1 : 0;
+        const int ll = lane - L3_OFF * p;
+        const int o = ll < 12 ? ll : 11;
         const float* row = c.ws + L::W3R + o * L::W3R_STRIDE;
         const float* act = c.act3 + p * xstride + (o >= 6 ? W + 4 : 0);
         float2 aA = make_float2(c.ws[L::B3 + o], 0.f), aB = make_float2(0.f, 0.f);
@@ -430,7 +446,7 @@ __device__ __forceinline__ void mlp_forward_n(const KParams& P, Warp<NU, W>& c, 
         float sp, sg;
         det_softplus_sigmoid_opt(out, sp, sg, tape);
         float* obp = p ? ob[1] : ob[0];
-        if (lane < 24) {
+        if (ll < 12) {
             if (o < 6) obp[o] = out;
             else {
                 obp[o] = s0 * sp;
@@ -685,7 +701,26 @@ __device__ __forceinline__ void mlp_backward_n(Warp<NU, W>& c, const float2 (&lo
         }
     }
     __syncwarp();
-    {
+    if constexpr (NP == 2) {
+        // lanes 0..NIN-1 serve problem 0, lanes 16..16+NIN-1 problem 1 (the others shadow the last row)
+        const int p = lane >= LZ_OFF ? 1 : 0;
+        const int ll = lane - LZ_OFF * p;
+        const int i = ll < NIN ? ll : NIN - 1;
+        const float* row = c.ws + L::W1T + i * L::PAIR_STRIDE;
+        const float* db = c.bufB + p * xstride;
+        float2 a[4];
+        a[0] = a[1] = a[2] = a[3] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            const float4 wv = lds4(row + 2 * j);
+            const float4 dv = lds4(db + 2 * j);
+            a[j & 3] = fma2_(xy(wv), xy(dv), a[j & 3]);
+            a[(j + 1) & 3] = fma2_(zw(wv), zw(dv), a[(j + 1) & 3]);
+        }
+        const float2 s = add2_(add2_(a[0], a[1]), add2_(a[2], a[3]));
+        float* lzp = p ? lzbuf[1] : lzbuf[0];
+        if (ll < NIN) lzp[i] = s.x + s.y;
+    } else {
         const int i = lane < NIN ? lane : NIN - 1;
         const float* row = c.ws + L::W1T + i * L::PAIR_STRIDE;
         float2 a[NP][4];

@@ -601,9 +601,13 @@ static KernelChoice make_choice() {
 // Compiled (nu, width, particles, teams-per-CTA) combinations.
 static const std::vector<KernelChoice>& choices() {
     static const std::vector<KernelChoice> v = {
+#ifdef SDEMPC_DEV_IRIS_ONLY   // quick experiment builds (tools/dev_build.sh): the bench shape only
+        make_choice<4, 32, 1, 8>(),
+#else
         make_choice<4, 32, 1, 8>(), make_choice<4, 32, 2, 4>(), make_choice<4, 32, 4, 2>(), make_choice<4, 32, 8, 1>(),
         make_choice<6, 32, 1, 8>(), make_choice<6, 32, 8, 1>(),
         make_choice<4, 64, 1, 8>(), make_choice<6, 64, 1, 8>(), make_choice<6, 64, 8, 1>(),
+#endif
     };
     return v;
 }

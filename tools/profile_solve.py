@@ -16,12 +16,13 @@ ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--vehicle", default="iris")
 ap.add_argument("--particles", type=int, default=1)
 ap.add_argument("--launches", type=int, default=1)
+ap.add_argument("--lib", default=None, help="alternative libsdempc build (tools/dev_build.sh)")
 a = ap.parse_args()
 cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{a.vehicle}_traj.yaml"))
 cfg = config.build_config(cfgd, max_iter=a.iters, rtol=0.0, atol=0.0, num_particles=a.particles)
 blob = model_io.synthetic_model(a.vehicle).to_blob()
 pr = synthetic.batched_problems(a.batch, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=0)
-s = solver.MPCSolver(cfg, blob)
+s = solver.MPCSolver(cfg, blob, lib_path=a.lib)
 u0, i0 = s.reset(a.batch)
 s.stage(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
 ms = s.launch_timed(a.launches, flush_l2=False)
