@@ -88,6 +88,13 @@ typedef struct sdempc_config {
     float init_stepsize, max_stepsize, coef, decrease_factor, increase_factor; /* yaml:76-80 */
     float atol, rtol;                /* yaml:72-73 */
     float beta_init;                 /* yaml:69 (informational: beta_1 = 1/4 = k/(k+3))    */
+    /* Soft input-rate constraint of the position-control configuration
+     * (cost_params.u_slew_constr / u_slew_constr_coeff, iris_sitl_posctrl_mpc.yaml:40-41): with
+     * ds = u_t[i] - u_{t-1}[i] and e = ds - hi (ds > hi), ds - lo (ds < lo), 0 otherwise, every stage adds
+     * u_slew_constr_coeff * e^2 per input.  Coefficient 0 disables the term. */
+    float u_slew_constr_coeff;
+    float u_slew_lo[SDEMPC_MAX_NU];
+    float u_slew_hi[SDEMPC_MAX_NU];
 } sdempc_config;
 
 /*

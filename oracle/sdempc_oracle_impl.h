@@ -341,6 +341,11 @@ static REAL FN(step_fwd)(const sdempc_config* c, const OMODEL* m, OSTEP* st, con
         REAL du = u[i] - (REAL)c->uref[i], ds = u[i] - uprev[i];
         l = FMA((REAL)c->uerr * du, du, l);
         l = FMA((REAL)c->u_slew_coeff * ds, ds, l);
+        if (c->u_slew_constr_coeff != 0.0f) {   /* soft rate constraint (sdempc.h): violation e of [lo, hi] */
+            const REAL hi = (REAL)c->u_slew_hi[i], lo = (REAL)c->u_slew_lo[i];
+            const REAL e = ds > hi ? ds - hi : (ds < lo ? ds - lo : (REAL)0);
+            l = FMA((REAL)c->u_slew_constr_coeff * e, e, l);
+        }
     }
     l = FMA((REAL)c->res_mult, sig2, l);
     return l;
@@ -444,7 +449,12 @@ static void FN(step_bwd)(const sdempc_config* c, const OMODEL* m, const OSTEP* s
     for (int i = 0; i < 3; ++i) lv[i] = FMA(R[i][2], lz[2], FMA(R[i][1], lz[1], FMA(R[i][0], lz[0], lv[i])));
     /* direct u terms */
     for (int i = 0; i < nu; ++i) {
-        const REAL ds = (g2 * (REAL)c->u_slew_coeff) * (u[i] - uprev[i]);
+        REAL ds = (g2 * (REAL)c->u_slew_coeff) * (u[i] - uprev[i]);
+        if (c->u_slew_constr_coeff != 0.0f) {
+            const REAL d = u[i] - uprev[i], hi = (REAL)c->u_slew_hi[i], lo = (REAL)c->u_slew_lo[i];
+            const REAL e = d > hi ? d - hi : (d < lo ? d - lo : (REAL)0);
+            ds = ds + (g2 * (REAL)c->u_slew_constr_coeff) * e;
+        }
         gu[i] = FMA(g2 * (REAL)c->uerr, u[i] - (REAL)c->uref[i], gu[i]) + ds;
         gprev[i] = -ds;
     }

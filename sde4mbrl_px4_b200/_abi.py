@@ -42,6 +42,7 @@ class Config(C.Structure):
         ("res_mult", _f), ("u_slew_coeff", _f),
         ("init_stepsize", _f), ("max_stepsize", _f), ("coef", _f), ("decrease_factor", _f),
         ("increase_factor", _f), ("atol", _f), ("rtol", _f), ("beta_init", _f),
+        ("u_slew_constr_coeff", _f), ("u_slew_lo", _f * MAX_NU), ("u_slew_hi", _f * MAX_NU),
     ]
 
 
@@ -103,7 +104,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SDEMPC_LIB") or LIB_PATH   # SDEMPC_LIB: experiment builds (tools/dev_build.sh)
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "

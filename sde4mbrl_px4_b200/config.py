@@ -18,7 +18,7 @@ from . import _abi
 
 # keys whose semantics live in the un-vendored upstream package and are not on the
 # two BASELINE config styles: parsed, kept in cfg_dict, not applied (DESIGN.md "out of scope").
-_UNSUPPORTED_COST_KEYS = ("u_slew_constr", "u_slew_constr_coeff", "res_sig")
+_UNSUPPORTED_COST_KEYS = ("res_sig",)
 _UNSUPPORTED_TOP_KEYS = ("state_constr", "use_sysId_model")
 
 
@@ -110,6 +110,16 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
             getattr(c, key)[i] = v
     c.res_mult = float(cp.get("res_mult", 0.0))
     c.u_slew_coeff = float(cp.get("u_slew_coeff", 0.0))
+    # soft input-rate constraint of the position-control YAML (iris_sitl_posctrl_mpc.yaml:40-41)
+    sc = cp.get("u_slew_constr", None)
+    c.u_slew_constr_coeff = float(cp.get("u_slew_constr_coeff", 0.0)) if sc is not None else 0.0
+    if sc is not None:
+        if len(sc) != nu or any(len(b) != 2 for b in sc):
+            raise ConfigError("cost_params.u_slew_constr must have one [lo, hi] pair per input")
+        for i, (lo, hi) in enumerate(sc):
+            if not float(lo) <= float(hi):
+                raise ConfigError("cost_params.u_slew_constr: lo must not exceed hi")
+            c.u_slew_lo[i], c.u_slew_hi[i] = float(lo), float(hi)
     c.init_stepsize = float(ls.get("init_stepsize", apg.get("stepsize", 1.0)))
     c.max_stepsize = float(ls.get("max_stepsize", 1.0))
     c.coef = float(ls.get("coef", 0.01))

@@ -41,6 +41,7 @@ struct KParams {
     float discount;
     float u_lo[SDEMPC_MAX_NU], u_hi[SDEMPC_MAX_NU], uref[SDEMPC_MAX_NU];
     float uerr, perr[3], verr[3], qerr[3], werr[3], res_mult, slew;
+    float slewc, slew_lo[SDEMPC_MAX_NU], slew_hi[SDEMPC_MAX_NU];   // soft rate constraint (0: off)
     float init_step, max_step, coef, dec_f, inc_f, atol, rtol;
     // rigid-body model
     float inv_m, grav, kT, kT2, J[3], Jinv[3], Jd[3], mixer[3][SDEMPC_MAX_NU], sig0[6];
@@ -343,6 +344,11 @@ __device__ __forceinline__ float phys_step(const KParams& P, int t, const float 
         const float du = u[i] - P.uref[i], ds = u[i] - up[i];
         l = fma_(P.uerr * du, du, l);
         l = fma_(P.slew * ds, ds, l);
+        if (P.slewc != 0.f) {   // soft rate constraint: violation e of [lo, hi]
+            const float hi = P.slew_hi[i], lo = P.slew_lo[i];
+            const float e = ds > hi ? ds - hi : (ds < lo ? ds - lo : 0.f);
+            l = fma_(P.slewc * e, e, l);
+        }
     }
     l = fma_(P.res_mult, sig2, l);
     return l;
@@ -786,7 +792,12 @@ __device__ __forceinline__ void bwd_post(const KParams& P, const float (&x)[NX],
     for (int i = 0; i < 3; ++i) m.lv[i] = fma_(R[i][2], lz[2], fma_(R[i][1], lz[1], fma_(R[i][0], lz[0], m.lv[i])));
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-        const float ds = (m.g2 * P.slew) * (u[i] - up[i]);
+        float ds = (m.g2 * P.slew) * (u[i] - up[i]);
+        if (P.slewc != 0.f) {
+            const float d = u[i] - up[i], hi = P.slew_hi[i], lo = P.slew_lo[i];
+            const float e = d > hi ? d - hi : (d < lo ? d - lo : 0.f);
+            ds = ds + (m.g2 * P.slewc) * e;
+        }
         gu[i] = fma_(m.g2 * P.uerr, u[i] - P.uref[i], gu[i]) + ds;
         const float gt = gu[i] + gp[i];
         gp[i] = -ds;

@@ -702,6 +702,8 @@ static void build_kparams(sdempc_handle* h) {
     k.uerr = c.uerr;
     for (int i = 0; i < 3; ++i) { k.perr[i] = c.perr[i]; k.verr[i] = c.verr[i]; k.qerr[i] = c.qerr[i]; k.werr[i] = c.werr[i]; }
     k.res_mult = c.res_mult; k.slew = c.u_slew_coeff;
+    k.slewc = c.u_slew_constr_coeff;
+    for (int i = 0; i < SDEMPC_MAX_NU; ++i) { k.slew_lo[i] = c.u_slew_lo[i]; k.slew_hi[i] = c.u_slew_hi[i]; }
     k.init_step = c.init_stepsize; k.max_step = c.max_stepsize; k.coef = c.coef; k.dec_f = c.decrease_factor;
     k.inc_f = c.increase_factor; k.atol = c.atol; k.rtol = c.rtol;
     // derived model constants: one IEEE float operation each (the oracle derives them identically)

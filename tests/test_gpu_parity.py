@@ -210,6 +210,39 @@ def test_nondefault_schedule_and_options(solver, O, mode):
     assert len(set(a[2][:, 2])) > 1         # early stops (no-improvement budget) at different iterations
 
 
+@pytest.mark.parametrize("mode", [{}, {"group": True}, {"sequential_ls": True}, {"num_particles": 2}])
+def test_soft_slew_rate_constraint(solver, O, mode):
+    """Position-control configuration with the reference's u_slew_constr (iris_sitl_posctrl_mpc.yaml:40-41),
+    tightened so that the constraint is active along the solve: cost, gradient and the free-running solve
+    match the oracle bit for bit on every kernel family."""
+    import os
+
+    from conftest import ROOT
+    from sde4mbrl_px4_b200 import config, model_io
+
+    cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_pos.yaml"))
+    cfgd["cost_params"]["u_slew_constr"] = [[-0.01, 0.004], [-0.02, 0.01], [-29, 0.002], [-0.005, 0.25]]
+    cfgd["apg_mpc"].update(max_iter=40)
+    cfg = config.build_config(cfgd, **mode)
+    blob = model_io.synthetic_model("iris").to_blob()
+    s, o = solver.MPCSolver(cfg, blob), O.Oracle(cfg, blob, "f32")
+    B = 19 if "num_particles" not in mode else 5
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=77)
+    u0, i0 = s.reset(B)
+    uq = np.clip(u0 + 0.05 * np.random.default_rng(2).standard_normal(u0.shape), 1e-4, 1).astype(np.float32)
+    xdes = pr["xref_win"][:, 0]
+    Ja, ga, _ = s.rollout(pr["x"], uq, u0[:, 0], xdes=xdes, rng=pr["rng"])
+    Jb, gb, _ = o.rollout(pr["x"], uq, u0[:, 0], xdes=xdes, rng=pr["rng"])
+    _eq(Ja, Jb, f"cost {mode}"); _eq(ga, gb, f"grad {mode}")
+    a = s.solve(pr["x"], uq, i0, xdes=xdes, rng=pr["rng"], want_trace=True)
+    b = o.solve(pr["x"], uq, i0, xdes=xdes, rng=pr["rng"], want_trace=True)
+    _eq(a[3], b[3], f"trace {mode}"); _eq(a[0], b[0], f"u* {mode}"); _eq(a[1], b[1], f"x_evol {mode}")
+    # the constraint matters: without it the same solve ends elsewhere
+    cfg.u_slew_constr_coeff = 0.0
+    c = O.Oracle(cfg, blob, "f32").solve(pr["x"], uq, i0, xdes=xdes, rng=pr["rng"])
+    assert not np.array_equal(c[0], b[0])
+
+
 @pytest.mark.parametrize("seed", list(range(24)))
 def test_randomised_configurations(solver, O, seed):
     """Seeded fuzz over the configuration space (horizon 4..32, step grid, discount, cost weights, bounds, line-search
@@ -233,6 +266,9 @@ def test_randomised_configurations(solver, O, seed):
         cp[k] = [float(v) for v in rng.uniform(0.1, 150.0, 3)]
     cp.update(uerr=float(rng.uniform(0, 2)), res_mult=float(rng.uniform(0, 0.5)), u_slew_coeff=float(rng.uniform(0, 2)),
               uref=[float(v) for v in rng.uniform(0.3, 0.8, nu)])
+    if seed % 3 == 0:   # soft input-rate constraint, tight enough to be active
+        cp.update(u_slew_constr=[[-float(a), float(b)] for a, b in zip(rng.uniform(0.005, 0.2, nu), rng.uniform(0.005, 0.2, nu))],
+                  u_slew_constr_coeff=float(rng.uniform(0.5, 20.0)))
     lo = rng.uniform(1e-4, 0.2, nu)
     cfgd["input_constr"]["input_bound"] = [[float(a), float(b)] for a, b in zip(lo, rng.uniform(0.85, 1.0, nu))]
     ls = cfgd["apg_mpc"]["linesearch"]

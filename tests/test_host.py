@@ -32,12 +32,21 @@ def test_reference_yaml_files_load_unchanged():
     assert len(files) == 6
     for f in files:
         d = config.load_yaml(f)
-        with pytest.warns(UserWarning) if "iris_sitl_posctrl" in f else _nullcontext():
-            c = config.build_config(d)
+        c = config.build_config(d, strict=True)   # every key of every reference YAML is applied
         assert c.horizon == 20 and c.nu in (4, 6) and c.num_particles == 1
         assert abs(config.time_steps(d)[0] - 0.05) < 1e-9
+        if "iris_sitl_posctrl" in f:              # the one file with a soft input-rate constraint (yaml:40-41)
+            assert c.u_slew_constr_coeff == 10.0 and np.allclose(list(c.u_slew_hi)[:4], [0.07, 0.32, 0.2, 0.25])
+            assert np.allclose(list(c.u_slew_lo)[:4], [-18, -26, -29, -10])
+        else:
+            assert c.u_slew_constr_coeff == 0.0
+    # keys whose semantics exist only upstream are still reported, and rejected under strict=True
+    d = config.load_yaml(files[0])
+    d["state_constr"] = {"state_id": [3]}
+    with pytest.warns(UserWarning):
+        config.build_config(d)
     with pytest.raises(config.ConfigError):
-        config.build_config(config.load_yaml(os.path.join(REF_LAUNCH, "iris_sitl_posctrl_mpc.yaml")), strict=True)
+        config.build_config(d, strict=True)
 
 
 class _nullcontext:

@@ -79,9 +79,9 @@ def _problem(cfg, B, seed):
     return pr, u, up
 
 
-@pytest.mark.parametrize("vehicle,P", [("iris", 1), ("iris", 4), ("hexa", 2)])
-def test_adjoint_vs_finite_differences(vehicle, P):
-    cfg, blob, _ = make_setup(vehicle, "traj", num_particles=P)
+@pytest.mark.parametrize("vehicle,mode,P", [("iris", "traj", 1), ("iris", "traj", 4), ("hexa", "traj", 2), ("iris", "pos", 1)])
+def test_adjoint_vs_finite_differences(vehicle, mode, P):
+    cfg, blob, _ = make_setup(vehicle, mode, num_particles=P)
     o = O.Oracle(cfg, blob, "f64")
     pr, u, up = _problem(cfg, 1, 11)
     u = u.astype(np.float64)
@@ -98,14 +98,14 @@ def test_adjoint_vs_finite_differences(vehicle, P):
         assert abs(fd - g[0, t, i]) <= 1e-6 * max(1.0, np.abs(g).max())
 
 
-@pytest.mark.parametrize("vehicle,P", [("iris", 2), ("hexa", 1)])
-def test_cost_and_adjoint_vs_torch_autograd(vehicle, P):
+@pytest.mark.parametrize("vehicle,mode,P", [("iris", "traj", 2), ("hexa", "traj", 1), ("iris", "pos", 1)])
+def test_cost_and_adjoint_vs_torch_autograd(vehicle, mode, P):
     """An independently written PyTorch float64 statement of J(u) gives the same cost and gradient."""
     import torch
 
     import torch_ref
 
-    cfg, blob, model = make_setup(vehicle, "traj", enu=False, num_particles=P)
+    cfg, blob, model = make_setup(vehicle, mode, enu=False, num_particles=P)
     o = O.Oracle(cfg, blob, "f64")
     pr, u, up = _problem(cfg, 1, 5)
     xi = np.random.default_rng(1).standard_normal((1, P, cfg.horizon, 6))
@@ -115,6 +115,32 @@ def test_cost_and_adjoint_vs_torch_autograd(vehicle, P):
     Jt.backward()
     assert abs(float(Jt) - J[0]) <= 1e-9 * abs(J[0])
     assert np.abs(ut.grad.numpy() - g[0]).max() <= 1e-8 * np.abs(g).max()
+
+
+def test_soft_slew_constraint_is_active_and_one_sided():
+    """iris_pos.yaml carries the reference's u_slew_constr (iris_sitl_posctrl_mpc.yaml:40-41): the penalty is
+    zero inside [lo, hi], quadratic in the violation outside, and switched off by a zero coefficient."""
+    cfg, blob, _ = make_setup("iris", "pos")
+    assert cfg.u_slew_constr_coeff == 10.0 and abs(cfg.u_slew_hi[0] - 0.07) < 1e-7 and cfg.u_slew_lo[3] == -10.0
+    o = O.Oracle(cfg, blob, "f64")
+    cfg0, _, _ = make_setup("iris", "pos")
+    cfg0.u_slew_constr_coeff = 0.0
+    o0 = O.Oracle(cfg0, blob, "f64")
+    pr, _, up = _problem(cfg, 1, 3)
+    H, nu = cfg.horizon, cfg.nu
+    base = np.tile(np.array(cfg.uref[:nu], np.float64), (1, H, 1))
+    kw = dict(xref_win=pr["xref_win"], rng=pr["rng"], want_grad=False)
+    # constant plan: no rate at all -> no penalty
+    assert o.rollout(pr["x"], base, up, **kw)[0][0] == o0.rollout(pr["x"], base, up, **kw)[0][0]
+    # a step of +0.1 on motor 0 at t = 5 violates hi = 0.07 by 0.03 once; the step back down (-0.1 at t = 6) is inside lo
+    u = base.copy()
+    u[0, 5, 0] += 0.1
+    dJ = o.rollout(pr["x"], u, up, **kw)[0][0] - o0.rollout(pr["x"], u, up, **kw)[0][0]
+    assert abs(dJ - 10.0 * 0.03 ** 2) < 1e-8   # hi is stored as float32
+    # the same step on motor 1 (hi = 0.32) stays inside the band
+    u = base.copy()
+    u[0, 5, 1] += 0.1
+    assert o.rollout(pr["x"], u, up, **kw)[0][0] == o0.rollout(pr["x"], u, up, **kw)[0][0]
 
 
 def test_f32_oracle_close_to_f64():

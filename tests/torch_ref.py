@@ -65,6 +65,11 @@ def cost(cfg, M, x0, u, uprev, xref, xi):
             l = (perr * (xn[0:3] - xr[0:3]) ** 2).sum() + (verr * (xn[3:6] - xr[3:6]) ** 2).sum() + (qerr * e ** 2).sum() \
                 + (werr * (xn[10:13] - xr[10:13]) ** 2).sum() + cfg.uerr * ((u[t] - uref) ** 2).sum() \
                 + cfg.u_slew_coeff * ((u[t] - up) ** 2).sum() + cfg.res_mult * (sig ** 2).sum()
+            if cfg.u_slew_constr_coeff != 0.0:   # soft rate constraint: squared violation of [lo, hi]
+                lo = torch.tensor(list(cfg.u_slew_lo[: cfg.nu]), dtype=torch.float64)
+                hi = torch.tensor(list(cfg.u_slew_hi[: cfg.nu]), dtype=torch.float64)
+                d = u[t] - up
+                l = l + cfg.u_slew_constr_coeff * ((torch.relu(d - hi) - torch.relu(lo - d)) ** 2).sum()
             J = J + disc * l
             disc *= cfg.discount
             x = xn
