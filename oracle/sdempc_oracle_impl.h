@@ -341,11 +341,6 @@ static REAL FN(step_fwd)(const sdempc_config* c, const OMODEL* m, OSTEP* st, con
         REAL du = u[i] - (REAL)c->uref[i], ds = u[i] - uprev[i];
         l = FMA((REAL)c->uerr * du, du, l);
         l = FMA((REAL)c->u_slew_coeff * ds, ds, l);
-        if (c->u_slew_constr_coeff != 0.0f) {   /* soft rate constraint (sdempc.h): violation e of [lo, hi] */
-            const REAL hi = (REAL)c->u_slew_hi[i], lo = (REAL)c->u_slew_lo[i];
-            const REAL e = ds > hi ? ds - hi : (ds < lo ? ds - lo : (REAL)0);
-            l = FMA((REAL)c->u_slew_constr_coeff * e, e, l);
-        }
     }
     l = FMA((REAL)c->res_mult, sig2, l);
     return l;
@@ -449,12 +444,7 @@ static void FN(step_bwd)(const sdempc_config* c, const OMODEL* m, const OSTEP* s
     for (int i = 0; i < 3; ++i) lv[i] = FMA(R[i][2], lz[2], FMA(R[i][1], lz[1], FMA(R[i][0], lz[0], lv[i])));
     /* direct u terms */
     for (int i = 0; i < nu; ++i) {
-        REAL ds = (g2 * (REAL)c->u_slew_coeff) * (u[i] - uprev[i]);
-        if (c->u_slew_constr_coeff != 0.0f) {
-            const REAL d = u[i] - uprev[i], hi = (REAL)c->u_slew_hi[i], lo = (REAL)c->u_slew_lo[i];
-            const REAL e = d > hi ? d - hi : (d < lo ? d - lo : (REAL)0);
-            ds = ds + (g2 * (REAL)c->u_slew_constr_coeff) * e;
-        }
+        const REAL ds = (g2 * (REAL)c->u_slew_coeff) * (u[i] - uprev[i]);
         gu[i] = FMA(g2 * (REAL)c->uerr, u[i] - (REAL)c->uref[i], gu[i]) + ds;
         gprev[i] = -ds;
     }
@@ -490,6 +480,36 @@ static void FN(traj_interp)(const float* tab, int T, REAL t, REAL* out) {
     FN(quat_renorm)(out + 6);
 }
 
+/* ---- soft input-rate constraint (include/sdempc.h) -------------------------------------
+ * A function of the control sequence only: J_rate = sum_i w_t e_i^2 over i = (t, k), accumulated as 32
+ * strided partials + butterfly; dJ_rate/du_i = 2 w_t e_i - 2 w_{t+1} e_{i+nu}; w_t = coeff * discount^t
+ * (running product), e_i = violation of [lo, hi] by u_t[k] - u_{t-1}[k].  Added to every particle's cost
+ * and gradient. */
+static REAL FN(butterfly)(REAL* p);
+static REAL FN(rate_violation)(const sdempc_config* c, int nu, const REAL* u, const REAL* uprev0, int t, int k) {
+    const REAL ds = u[t * nu + k] - (t == 0 ? uprev0[k] : u[(t - 1) * nu + k]);
+    const REAL hi = (REAL)c->u_slew_hi[k], lo = (REAL)c->u_slew_lo[k];
+    return ds > hi ? ds - hi : (ds < lo ? ds - lo : (REAL)0);
+}
+static REAL FN(rate_terms)(const sdempc_config* c, int nu, const REAL* u, const REAL* uprev0, REAL* rgrad) {
+    const int H = c->horizon, n = H * nu;
+    REAL w[SDEMPC_MAX_H], part[32];
+    REAL disc = 1;
+    for (int t = 0; t < H; ++t) { w[t] = disc * (REAL)c->u_slew_constr_coeff; disc = disc * (REAL)c->discount; }
+    for (int l = 0; l < 32; ++l) part[l] = 0;
+    for (int i = 0; i < n; ++i) {
+        const int t = i / nu, k = i % nu;
+        const REAL e = FN(rate_violation)(c, nu, u, uprev0, t, k);
+        part[i & 31] = FMA(w[t] * e, e, part[i & 31]);
+        if (rgrad) {
+            REAL a = ((REAL)2 * w[t]) * e;
+            if (t + 1 < H) a = a - ((REAL)2 * w[t + 1]) * FN(rate_violation)(c, nu, u, uprev0, t + 1, k);
+            rgrad[i] = a;
+        }
+    }
+    return FN(butterfly)(part);
+}
+
 /* ---- rollout: J(u) and dJ/du --------------------------------------------------- */
 /* xref[H+1][13] internal frame; xi[P][H][6]; grad[H][nu] or NULL; xmean[H+1][13] or NULL. */
 static REAL FN(rollout)(const sdempc_config* c, const OMODEL* m, const REAL* x0, const REAL* u,
@@ -498,7 +518,9 @@ static REAL FN(rollout)(const sdempc_config* c, const OMODEL* m, const REAL* x0,
     const int H = c->horizon, nu = m->nu, P = c->num_particles;
     const REAL invP = (REAL)1 / (REAL)P;
     REAL J = 0;
-    REAL gpart[NUH];
+    REAL gpart[NUH], rgrad[NUH];
+    const int rate_on = c->u_slew_constr_coeff != 0.0f;
+    const REAL Jrate = rate_on ? FN(rate_terms)(c, nu, u, uprev0, grad ? rgrad : NULL) : (REAL)0;
     if (grad) for (int i = 0; i < H * nu; ++i) grad[i] = 0;
     if (xmean) for (int i = 0; i < (H + 1) * NX; ++i) xmean[i] = 0;
     for (int p = 0; p < P; ++p) {
@@ -515,6 +537,7 @@ static REAL FN(rollout)(const sdempc_config* c, const OMODEL* m, const REAL* x0,
             if (t + 1 < H) for (int i = 0; i < NX; ++i) steps[t + 1].x[i] = st->xn[i];
             disc = disc * (REAL)c->discount;
         }
+        if (rate_on) Jp = Jp + Jrate;
         J = (p == 0) ? Jp : J + Jp;
         if (xmean) {
             for (int i = 0; i < NX; ++i) xmean[i] = (p == 0) ? x0[i] : xmean[i] + x0[i];
@@ -535,6 +558,7 @@ static REAL FN(rollout)(const sdempc_config* c, const OMODEL* m, const REAL* x0,
                              xi + ((size_t)p * H + t) * 6, dt, sdt, lam, gu, gn);
                 for (int i = 0; i < nu; ++i) { gpart[t * nu + i] = gu[i] + gp[i]; gp[i] = gn[i]; }
             }
+            if (rate_on) for (int i = 0; i < H * nu; ++i) gpart[i] = gpart[i] + rgrad[i];
             for (int i = 0; i < H * nu; ++i) grad[i] = (p == 0) ? gpart[i] : grad[i] + gpart[i];
         }
     }

@@ -100,6 +100,14 @@ __device__ __forceinline__ float g_rollout_fwd(const KParams& P, Warp<NU, W>& c,
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
     }
     __syncwarp();
+    if (SDEMPC_RATE_ON(P)) {   // soft input-rate constraint of the problems in the pass (mpc_kernels.cuh)
+        for (unsigned m = mask; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            const float* rb = gw.reg(b);
+            const float v = rate_cost<NU>(P, lane, rb + useq_off, rb + P.o_uprev);
+            if (lane == b) Jp = Jp + v;
+        }
+    }
     return Jp;
 }
 
@@ -171,6 +179,13 @@ __device__ __forceinline__ void g_rollout_bwd(const KParams& P, Warp<NU, W>& c, 
         }
     }
     __syncwarp();
+    if (SDEMPC_RATE_ON(P)) {
+        for (unsigned m = mask; m; m &= m - 1) {
+            float* rb = gw.reg(__ffs(m) - 1);
+            rate_grad_add<NU>(P, lane, rb + useq_off, rb + P.o_uprev, rb + P.o_g);
+        }
+        __syncwarp();
+    }
 }
 
 // APG solves of the warp's problems (lane b = problem b).  On entry xk of every problem holds the shifted,

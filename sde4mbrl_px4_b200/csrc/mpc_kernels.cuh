@@ -42,6 +42,7 @@ struct KParams {
     float u_lo[SDEMPC_MAX_NU], u_hi[SDEMPC_MAX_NU], uref[SDEMPC_MAX_NU];
     float uerr, perr[3], verr[3], qerr[3], werr[3], res_mult, slew;
     float slewc, slew_lo[SDEMPC_MAX_NU], slew_hi[SDEMPC_MAX_NU];   // soft rate constraint (0: off)
+    float rate_w[SDEMPC_MAX_H];                                    // slewc * discount^t (float products, host)
     float init_step, max_step, coef, dec_f, inc_f, atol, rtol;
     // rigid-body model
     float inv_m, grav, kT, kT2, J[3], Jinv[3], Jd[3], mixer[3][SDEMPC_MAX_NU], sig0[6];
@@ -109,6 +110,11 @@ struct Layout {
     static constexpr int SMEM_FLOATS = WREG ? PART_A : TOTAL;
 };
 
+#ifdef SDEMPC_NO_RATE   // experiment builds only: compile the soft rate constraint out
+#define SDEMPC_RATE_ON(P) false
+#else
+#define SDEMPC_RATE_ON(P) ((P).slewc != 0.f)
+#endif
 #ifndef SDEMPC_L3_OFF
 #define SDEMPC_L3_OFF 16
 #endif
@@ -344,14 +350,45 @@ __device__ __forceinline__ float phys_step(const KParams& P, int t, const float 
         const float du = u[i] - P.uref[i], ds = u[i] - up[i];
         l = fma_(P.uerr * du, du, l);
         l = fma_(P.slew * ds, ds, l);
-        if (P.slewc != 0.f) {   // soft rate constraint: violation e of [lo, hi]
-            const float hi = P.slew_hi[i], lo = P.slew_lo[i];
-            const float e = ds > hi ? ds - hi : (ds < lo ? ds - lo : 0.f);
-            l = fma_(P.slewc * e, e, l);
-        }
     }
     l = fma_(P.res_mult, sig2, l);
     return l;
+}
+
+// ---------------------------------------------------------------------------------
+// Soft input-rate constraint (include/sdempc.h; iris_sitl_posctrl_mpc.yaml:40-41).  It depends on the control
+// sequence only, so it is evaluated once per rollout as a warp-shaped vector operation instead of inside every
+// step: J += sum_i w_t e_i^2 (32 strided partials + butterfly), g_i += 2 w_t e_i - 2 w_{t+1} e_{i+NU}, with
+// e_i the violation of [lo, hi] by u_t[k] - u_{t-1}[k] and w_t = rate_w[t].  All lanes of the warp take part.
+// ---------------------------------------------------------------------------------
+template <int NU>
+__device__ __forceinline__ float rate_violation(const KParams& P, const float* useq, const float* uprev, int t, int k) {
+    const float ds = useq[t * NU + k] - (t == 0 ? uprev[k] : useq[(t - 1) * NU + k]);
+    const float hi = P.slew_hi[k], lo = P.slew_lo[k];
+    return ds > hi ? ds - hi : (ds < lo ? ds - lo : 0.f);
+}
+
+template <int NU>
+__device__ __forceinline__ float rate_cost(const KParams& P, int lane, const float* useq, const float* uprev) {
+    const int n = P.H * NU;
+    float part = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        const int t = i / NU, k = i % NU;
+        const float e = rate_violation<NU>(P, useq, uprev, t, k);
+        part = fma_(P.rate_w[t] * e, e, part);
+    }
+    return warp_butterfly(part);
+}
+
+template <int NU>
+__device__ __forceinline__ void rate_grad_add(const KParams& P, int lane, const float* useq, const float* uprev, float* g) {
+    const int n = P.H * NU;
+    for (int i = lane; i < n; i += 32) {
+        const int t = i / NU, k = i % NU;
+        float a = (2.f * P.rate_w[t]) * rate_violation<NU>(P, useq, uprev, t, k);
+        if (t + 1 < P.H) a = a - (2.f * P.rate_w[t + 1]) * rate_violation<NU>(P, useq, uprev, t + 1, k);
+        g[i] = g[i] + a;
+    }
 }
 
 // Both networks for NP problems at once (lane j = hidden unit j; NP independent dependency chains are
@@ -560,6 +597,7 @@ __device__ __forceinline__ float rollout_fwd(const KParams& P, Warp<NU, W>& c, c
         for (int i = 0; i < NU; ++i) up[i] = u[i];
     }
     if constexpr (MODE != 0) __syncwarp();   // lane 0's last tape writes are visible to every lane that reads the tape next
+    if (SDEMPC_RATE_ON(P)) Jp = Jp + rate_cost<NU>(P, c.lane, useq, c.uprev);
     return Jp;
 }
 
@@ -792,12 +830,7 @@ __device__ __forceinline__ void bwd_post(const KParams& P, const float (&x)[NX],
     for (int i = 0; i < 3; ++i) m.lv[i] = fma_(R[i][2], lz[2], fma_(R[i][1], lz[1], fma_(R[i][0], lz[0], m.lv[i])));
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-        float ds = (m.g2 * P.slew) * (u[i] - up[i]);
-        if (P.slewc != 0.f) {
-            const float d = u[i] - up[i], hi = P.slew_hi[i], lo = P.slew_lo[i];
-            const float e = d > hi ? d - hi : (d < lo ? d - lo : 0.f);
-            ds = ds + (m.g2 * P.slewc) * e;
-        }
+        const float ds = (m.g2 * P.slew) * (u[i] - up[i]);
         gu[i] = fma_(m.g2 * P.uerr, u[i] - P.uref[i], gu[i]) + ds;
         const float gt = gu[i] + gp[i];
         gp[i] = -ds;
@@ -860,6 +893,10 @@ __device__ __forceinline__ void rollout_bwd(const KParams& P, Warp<NU, W>& c, co
         }
     }
     __syncwarp();
+    if (SDEMPC_RATE_ON(P)) {
+        rate_grad_add<NU>(P, lane, useq, c.uprev, c.g);
+        __syncwarp();
+    }
 }
 
 // ---------------------------------------------------------------------------------

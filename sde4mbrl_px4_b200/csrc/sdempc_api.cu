@@ -603,6 +603,9 @@ static const std::vector<KernelChoice>& choices() {
     static const std::vector<KernelChoice> v = {
 #ifdef SDEMPC_DEV_IRIS_ONLY   // quick experiment builds (tools/dev_build.sh): the bench shape only
         make_choice<4, 32, 1, 8>(),
+#ifdef SDEMPC_DEV_HEXA
+        make_choice<6, 64, 1, 8>(),
+#endif
 #else
         make_choice<4, 32, 1, 8>(), make_choice<4, 32, 2, 4>(), make_choice<4, 32, 4, 2>(), make_choice<4, 32, 8, 1>(),
         make_choice<6, 32, 1, 8>(), make_choice<6, 32, 8, 1>(),
@@ -703,6 +706,10 @@ static void build_kparams(sdempc_handle* h) {
     for (int i = 0; i < 3; ++i) { k.perr[i] = c.perr[i]; k.verr[i] = c.verr[i]; k.qerr[i] = c.qerr[i]; k.werr[i] = c.werr[i]; }
     k.res_mult = c.res_mult; k.slew = c.u_slew_coeff;
     k.slewc = c.u_slew_constr_coeff;
+    {   // stage weights of the rate constraint: the running float product discount^t times the coefficient
+        float disc = 1.0f;
+        for (int t = 0; t < SDEMPC_MAX_H; ++t) { k.rate_w[t] = disc * c.u_slew_constr_coeff; disc = disc * c.discount; }
+    }
     for (int i = 0; i < SDEMPC_MAX_NU; ++i) { k.slew_lo[i] = c.u_slew_lo[i]; k.slew_hi[i] = c.u_slew_hi[i]; }
     k.init_step = c.init_stepsize; k.max_step = c.max_stepsize; k.coef = c.coef; k.dec_f = c.decrease_factor;
     k.inc_f = c.increase_factor; k.atol = c.atol; k.rtol = c.rtol;
