@@ -23,6 +23,7 @@ F_SPECULATIVE_LS = 4
 F_SEQUENTIAL_LS = 8
 F_GROUP = 16
 F_NO_CLUSTER = 32
+F_TENSOR = 64
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4
 

@@ -81,6 +81,8 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
         flags |= _abi.F_GROUP
     if overrides.get("no_cluster", False):
         flags |= _abi.F_NO_CLUSTER
+    if overrides.get("tensor", False):
+        flags |= _abi.F_TENSOR
     c.flags = flags
     for t, v in enumerate(time_steps(cfg)):
         c.dt[t] = float(v)

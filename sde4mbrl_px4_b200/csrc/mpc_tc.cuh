@@ -1,0 +1,288 @@
+// mpc_tc.cuh — tensor-core variant of the batched forward rollout (cost evaluation), tcgen05 + TMEM.
+//
+// Mapping: one CTA of 128 threads owns 128 rollouts; thread i is rollout (row) i and TMEM lane i.  The rigid
+// body, the cost and the noise run per thread with the state in registers (every lane useful), and each network
+// layer is ONE dense contraction over the CTA's rows on the 5th-generation tensor cores:
+//     D[128 x N] (TMEM, fp32) = A[128 x K] (TMEM, written by the rows' own threads with tcgen05.st) * B[N x K]^T
+// with B = the layer's weights for BOTH networks staged once in shared memory (K-major, no swizzle, bias folded
+// in as an extra input that is constant one; layer 2 and the output layer are block diagonal over
+// [drift | diffusion] columns).  kind::tf32: operands are read as TF32 (10-bit mantissa), accumulation is fp32,
+// so this path is NOT SPEC-ARITH: it is compared with the oracle at a stated tolerance (tests/test_gpu_parity.py,
+// DESIGN.md section 5), never bit for bit.  tanh is tanh.approx.f32 (same error class as the TF32 products).
+// Per step: st(z) -> MMA -> ld/tanh/st -> MMA -> ld/tanh/st -> MMA -> ld -> softplus, rigid body, cost.
+// tools/tc_probe.cu is the isolated check of the descriptor / TMEM conventions used here.
+#pragma once
+#include "mpc_kernels.cuh"
+
+namespace sdempc {
+
+template <int NU, int W>
+struct TCLayout {
+    static constexpr int NIN = 6 + NU;
+    static constexpr int N12 = 2 * W;                      // hidden columns: [drift units | diffusion units]
+    static constexpr int K1 = ((NIN + 1 + 7) / 8) * 8;     // inputs + the constant one, padded to the MMA K (8)
+    static constexpr int K2 = N12 + 8;                     // hidden + the constant one + 7 zeros
+    static constexpr int N3 = 16;                          // 6 + 6 outputs, padded
+    // operand images: [rows / 8][K / 4 chunks][8 rows][16 bytes]
+    static constexpr int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128, LBO = 128;
+    static constexpr int B1 = 0;
+    static constexpr int B2 = B1 + (N12 / 8) * SBO1;
+    static constexpr int B3 = B2 + (N12 / 8) * SBO2;
+    static constexpr int BYTES = B3 + (N3 / 8) * SBO2;
+    // tensor-memory columns (fp32 each)
+    static constexpr int C_D12 = 0, C_D3 = N12, C_A = N12 + 32;
+    static constexpr int COLS = (C_A + K2) <= 256 ? 256 : 512;
+    static_assert(C_A + K2 <= 512, "tensor memory columns");
+    __host__ __device__ static constexpr int off(int sbo, int row, int k) { return (row / 8) * sbo + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4; }
+};
+
+namespace tc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t desc(uint32_t saddr, int sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((128 >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 slice
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(db),
+                 "r"(idesc), "r"(acc), "r"(0u));
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nTCW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TCD;\nbra TCW;\nTCD:\n}\n" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, float (&o)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                 "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                 "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])));
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+                 "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])));
+}
+// all rows have written their operand: make it visible to the tensor core, then one thread issues
+__device__ __forceinline__ void publish() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+}  // namespace tc
+
+// reference row t (internal frame) of problem b: explicit window, trajectory time or fixed set-point
+__device__ __forceinline__ void tc_ref_row(const KParams& P, int b, int t, float (&row)[NX]) {
+    const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
+    if (P.xref_win != nullptr || P.xdes != nullptr) {
+        const float* src = P.xref_win ? P.xref_win + ((size_t)b * (P.H + 1) + t) * NX : P.xdes + (size_t)b * NX;
+        float tmp[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tmp[i] = __ldg(src + i);
+        if (enu) enu_ned(tmp, row);
+        else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) row[i] = tmp[i];
+        }
+    } else {
+        float tt = __ldg(P.curr_t + b);
+        for (int s = 0; s < t; ++s) tt = tt + P.dt[s];
+        traj_interp(P.traj, P.T, tt, row);
+    }
+}
+
+// Body of the kernel (entry point in sdempc_api.cu).  wimg: TCLayout image in global memory.
+template <int NU, int W>
+__device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char* sB, uint32_t* tmem_base_slot, uint64_t* bar) {
+    using L = TCLayout<NU, W>;
+    constexpr int NIN = L::NIN, N12 = L::N12;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // ---- one-time setup: weights to shared memory, barrier, tensor memory ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(P.wimg);
+        uint4* dst = reinterpret_cast<uint4*>(sB);
+        for (int i = tid; i < L::BYTES / 16; i += 128) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_slot)), "r"((uint32_t)L::COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic-proxy stores) -> tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = *tmem_base_slot;
+    const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
+    const uint32_t sb = tc::smem_u32(sB);
+    const uint32_t id12 = tc::idesc_tf32(128, N12), id3 = tc::idesc_tf32(128, L::N3);
+    uint32_t phase = 0;
+
+    const int row = blockIdx.x * 128 + tid;
+    const bool valid = row < P.B;
+    const int b = valid ? row : P.B - 1;   // rows past the batch shadow the last problem and store nothing
+    const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
+    float x[NX];
+    {
+        float tmp[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) tmp[i] = __ldg(P.x + (size_t)b * NX + i);
+        if (enu) enu_ned(tmp, x);
+        else {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = tmp[i];
+        }
+    }
+    if (valid && P.x_evol != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) P.x_evol[(size_t)b * (P.H + 1) * NX + i] = __ldg(P.x + (size_t)b * NX + i);
+    }
+    float up[NU], u[NU];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) up[i] = __ldg(P.uprev_in + (size_t)b * NU + i);
+    {   // the constant-one chunk of the layer-2 / output-layer operand
+        const float one8[8] = {1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        tc::st8(lane_addr + L::C_A + N12, one8);
+    }
+    const unsigned long long seed = P.rng ? P.rng[2 * (size_t)b] : 0ull, tick = P.rng ? P.rng[2 * (size_t)b + 1] : 0ull;
+    float Jp = 0.f, disc = 1.f;
+    for (int t = 0; t < P.H; ++t) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = __ldg(P.u_in + ((size_t)b * P.H + t) * NU + i);
+        // ---- layer 1 operand: [z, 1, 0 ...] ----
+        {
+            float z[NIN];
+            phys_features<NU>(x, u, z);
+#pragma unroll
+            for (int c0 = 0; c0 < L::K1; c0 += 8) {
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = (c0 + i < NIN) ? z[(c0 + i < NIN) ? c0 + i : 0] : (c0 + i == NIN ? 1.f : 0.f);
+                tc::st8(lane_addr + L::C_A + c0, a);
+            }
+        }
+        tc::publish();
+        if (tid == 0) {
+#pragma unroll
+            for (int k8 = 0; k8 < L::K1 / 8; ++k8)
+                tc::mma_ts(tb + L::C_D12, tb + L::C_A + 8 * k8, tc::desc(sb + L::B1 + k8 * 2 * L::LBO, L::SBO1), id12, k8 > 0);
+            tc::commit(bar);
+        }
+        tc::wait(bar, phase); phase ^= 1;
+        // ---- tanh -> layer 2 operand ----
+#pragma unroll
+        for (int c0 = 0; c0 < N12; c0 += 16) {
+            float v[16];
+            tc::ld16(lane_addr + L::C_D12 + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = tc::tanh_approx(v[i]);
+            tc::st16(lane_addr + L::C_A + c0, v);
+        }
+        tc::publish();
+        if (tid == 0) {
+#pragma unroll
+            for (int k8 = 0; k8 < L::K2 / 8; ++k8)
+                tc::mma_ts(tb + L::C_D12, tb + L::C_A + 8 * k8, tc::desc(sb + L::B2 + k8 * 2 * L::LBO, L::SBO2), id12, k8 > 0);
+            tc::commit(bar);
+        }
+        tc::wait(bar, phase); phase ^= 1;
+#pragma unroll
+        for (int c0 = 0; c0 < N12; c0 += 16) {
+            float v[16];
+            tc::ld16(lane_addr + L::C_D12 + c0, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = tc::tanh_approx(v[i]);
+            tc::st16(lane_addr + L::C_A + c0, v);
+        }
+        tc::publish();
+        if (tid == 0) {
+#pragma unroll
+            for (int k8 = 0; k8 < L::K2 / 8; ++k8)
+                tc::mma_ts(tb + L::C_D3, tb + L::C_A + 8 * k8, tc::desc(sb + L::B3 + k8 * 2 * L::LBO, L::SBO2), id3, k8 > 0);
+            tc::commit(bar);
+        }
+        tc::wait(bar, phase); phase ^= 1;
+        float r6[6], sig[6];
+        {
+            float o[16];
+            tc::ld16(lane_addr + L::C_D3, o);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                r6[i] = o[i];
+                float sp, sg;
+                det_softplus_sigmoid_opt(o[6 + i], sp, sg, false);
+                sig[i] = P.sig0[i] * sp;
+            }
+        }
+        // ---- noise, reference row, rigid body + Euler-Maruyama + cost ----
+        float xi[6], xr[NX], xn[NX], rn;
+        if (P.xi_override != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) xi[i] = __ldg(P.xi_override + ((size_t)b * P.H + t) * 6 + i);
+        } else {
+            const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+            const uint32_t c2 = (uint32_t)tick, c3 = ((uint32_t)(tick >> 32)) & 0x3FFFFFFFu;
+            uint32_t r[4];
+            philox4x32_10((uint32_t)t, 0u, c2, c3, k0, k1, r);
+            box_muller(r[0], r[1], xi[0], xi[1]);
+            box_muller(r[2], r[3], xi[2], xi[3]);
+            philox4x32_10((uint32_t)t, 0u, c2, c3 | (1u << 30), k0, k1, r);
+            box_muller(r[0], r[1], xi[4], xi[5]);
+        }
+        tc_ref_row(P, b, t + 1, xr);
+        const float l = phys_step<NU>(P, t, x, u, up, r6, sig, xi, xr, xn, rn);
+        Jp = fma_(disc, l, Jp);
+        disc = disc * P.discount;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) up[i] = u[i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = xn[i];
+        if (valid && P.x_evol != nullptr) {
+            float rowv[NX], o[NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) rowv[i] = xn[i];
+            quat_renorm(rowv + 6);
+            if (enu) enu_ned(rowv, o);
+            else {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) o[i] = rowv[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) P.x_evol[((size_t)b * (P.H + 1) + t + 1) * NX + i] = o[i];
+        }
+    }
+    if (valid) P.cost_out[b] = Jp;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"((uint32_t)L::COLS));
+}
+
+}  // namespace sdempc

@@ -20,6 +20,7 @@
 #include "mpc_group.cuh"
 #include "mpc_kernels.cuh"
 #include "mpc_pcluster.cuh"
+#include "mpc_tc.cuh"
 
 using namespace sdempc;
 
@@ -531,6 +532,15 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
     }
 }
 
+// Tensor-core batched forward rollout (mpc_tc.cuh): 128 rollouts per CTA, thread = rollout = TMEM lane.  P = 1.
+template <int NU, int W>
+__global__ void __launch_bounds__(128, 1) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    __shared__ uint32_t tmem_slot;
+    __shared__ __align__(8) uint64_t tc_bar;
+    tc_rollout_body<NU, W>(P, tc_smem, &tmem_slot, &tc_bar);
+}
+
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -566,6 +576,8 @@ struct KernelChoice {
     void (*closed_cl)(KParams);
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
+    void (*rollout_tc)(KParams);   // tensor-core forward rollout (P == 1), SDEMPC_F_TENSOR
+    int tc_bytes;
     int gp;
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
@@ -584,6 +596,12 @@ static KernelChoice make_choice() {
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     k.solve_pc = nullptr;
+    k.rollout_tc = nullptr;
+    k.tc_bytes = 0;
+    if constexpr (PP == 1) {
+        k.rollout_tc = mpc_tc_rollout_kernel<NU, W>;
+        k.tc_bytes = TCLayout<NU, W>::BYTES;
+    }
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
     k.gp = group_gp(NU, W);
     if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
@@ -626,6 +644,8 @@ struct sdempc_handle {
     KernelChoice kc;
     KParams kp;                       // template (config + model + layout)
     KParams kp_group;                 // same with the per-problem layout of the group kernel
+    std::vector<float> wimg_tc;       // tensor-core operand image (TCLayout)
+    float* d_wimg_tc = nullptr;
     size_t smem_bytes_group = 0;
     size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
@@ -686,6 +706,39 @@ static void pack_weights(sdempc_handle* h) {
             for (int o = 0; o < 6; ++o) I[W3C + j * 12 + 2 * o + n] = W3[n][o * W + j];
             I[B1 + 2 * j + n] = b1[n][j];
             I[B2 + 2 * j + n] = b2[n][j];
+        }
+    }
+}
+
+// Operand image of the tensor-core path (TCLayout in mpc_tc.cuh): K-major rows of [W1 | b1], block-diagonal
+// [W2 | b2] and [W3 | b3] over the [drift | diffusion] hidden columns; the bias multiplies a constant-one input.
+static void pack_weights_tc(sdempc_handle* h) {
+    const int NU = h->mh.nu, W = h->mh.width, NIN = 6 + NU, N12 = 2 * W;
+    const int K1 = ((NIN + 1 + 7) / 8) * 8, K2 = N12 + 8, N3 = 16;
+    const int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128;
+    const int B1 = 0, B2 = B1 + (N12 / 8) * SBO1, B3 = B2 + (N12 / 8) * SBO2, BYTES = B3 + (N3 / 8) * SBO2;
+    auto off = [](int sbo, int row, int k) { return ((row / 8) * sbo + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4) / 4; };
+    h->wimg_tc.assign(BYTES / 4, 0.f);
+    float* I = h->wimg_tc.data();
+    const float* p = h->weights.data();
+    for (int n = 0; n < 2; ++n) {
+        const float* W1 = p; p += (size_t)W * NIN;
+        const float* b1 = p; p += W;
+        const float* W2 = p; p += (size_t)W * W;
+        const float* b2 = p; p += W;
+        const float* W3 = p; p += 6 * (size_t)W;
+        const float* b3 = p; p += 6;
+        for (int j = 0; j < W; ++j) {
+            const int row = n * W + j;
+            for (int k = 0; k < NIN; ++k) I[B1 / 4 + off(SBO1, row, k)] = W1[j * NIN + k];
+            I[B1 / 4 + off(SBO1, row, NIN)] = b1[j];
+            for (int k = 0; k < W; ++k) I[B2 / 4 + off(SBO2, row, n * W + k)] = W2[j * W + k];
+            I[B2 / 4 + off(SBO2, row, N12)] = b2[j];
+        }
+        for (int o = 0; o < 6; ++o) {
+            const int row = n * 6 + o;
+            for (int k = 0; k < W; ++k) I[B3 / 4 + off(SBO2, row, n * W + k)] = W3[o * W + k];
+            I[B3 / 4 + off(SBO2, row, N12)] = b3[o];
         }
     }
 }
@@ -806,6 +859,11 @@ static int ensure_device(sdempc_handle* h) {
         if (h->smem_bytes_group > (size_t)prop.sharedMemPerBlockOptin) h->kc.solve_group = nullptr;   // does not fit: use one warp per problem
         else CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_group));
     }
+    if (h->kc.rollout_tc) {
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes));
+        CUDA_TRY(cudaMalloc(&h->d_wimg_tc, h->wimg_tc.size() * 4));
+        CUDA_TRY(cudaMemcpy(h->d_wimg_tc, h->wimg_tc.data(), h->wimg_tc.size() * 4, cudaMemcpyHostToDevice));
+    }
     cudaFuncAttributes fa;
     CUDA_TRY(cudaFuncGetAttributes(&fa, h->kc.solve));
     h->regs = fa.numRegs;
@@ -848,7 +906,7 @@ static bool use_group(const sdempc_handle* h, int B) {
 static int ensure_mtape_group(sdempc_handle* h, int grid) {
     const size_t tapes = (size_t)grid * GROUP_GW * h->kc.gp;
     if (tapes <= h->mtape_group_n) return 0;
-    if (h->d_mtape_group) cudaFree(h->d_mtape_group);
+    if (h->d_mtape_group) cudaFree(h->d_mtape_group); cudaFree(h->d_wimg_tc);
     h->d_mtape_group = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_mtape_group, tapes * (size_t)h->cfg.horizon * 2 * h->mh.width * sizeof(float2)));
     h->mtape_group_n = tapes;
@@ -1047,6 +1105,7 @@ int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbyte
     h->weights.resize(2 * per_net);
     memcpy(h->weights.data(), (const char*)model_blob + sizeof mh, 2 * per_net * 4);
     pack_weights(h);
+    if (h->kc.rollout_tc) pack_weights_tc(h);
     build_kparams(h);
     *out = h;
     return 0;
@@ -1258,11 +1317,27 @@ int sdempc_rollout(sdempc_t* h, int B, const float* x, const float* curr_t, cons
     k.cost_out = po.reserve<float>((size_t)B);
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = h->d_mtape;
     h->staged_ok = false;
-    if ((rc = launch(h, h->kc.rollout, k, grid))) return rc;
-    h->last_grid = grid;
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    if (h->cfg.flags & SDEMPC_F_TENSOR) {
+        // tensor-core path: explicit opt-in, never a silent substitute (it is not SPEC-ARITH: TF32 products)
+        if (!h->kc.rollout_tc || P != 1 || grad != nullptr || h->cfg.u_slew_constr_coeff != 0.0f)
+            return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core rollout evaluates costs only (grad == NULL), with one particle and "
+                                       "no input-rate constraint");
+        k.wimg = h->d_wimg_tc;
+        const int tgrid = (B + 127) / 128;
+        void* args[] = {&k};
+        CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(h->kc.rollout_tc), dim3(tgrid), dim3(128), args, (size_t)h->kc.tc_bytes, h->stream));
+        h->launches += 1;
+        h->last_grid = tgrid;
+    } else {
+        if ((rc = launch(h, h->kc.rollout, k, grid))) return rc;
+        h->last_grid = grid;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, po.off, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     const size_t o_p = a16((size_t)B * (H + 1) * NX * 4), o_c = o_p + a16((size_t)B * n * 4);
     if (x_evol) memcpy(x_evol, h->h_out, (size_t)B * (H + 1) * NX * 4);
     if (grad) memcpy(grad, h->h_out + o_p, (size_t)B * n * 4);

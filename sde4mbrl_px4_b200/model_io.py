@@ -111,9 +111,9 @@ VEHICLES = {
 
 
 def synthetic_model(vehicle: str = "iris", seed: int = 0, width: int | None = None,
-                    weight_scale: float = 0.1) -> SDEModel:
+                    weight_scale: float = 0.1, bias_scale: float = 0.0) -> SDEModel:
     """Seeded synthetic learned model: hover-capable plant,
-    MLP weights N(0, (weight_scale/sqrt(fan_in))^2), zero biases."""
+    MLP weights N(0, (weight_scale/sqrt(fan_in))^2), biases N(0, bias_scale^2) (zero by default)."""
     v = VEHICLES[vehicle]
     nu, W = v["nu"], int(width or v["width"])
     g = 9.81
@@ -124,6 +124,11 @@ def synthetic_model(vehicle: str = "iris", seed: int = 0, width: int | None = No
         for lay, (o, i) in (("1", (W, n_in)), ("2", (W, W)), ("3", (6, W))):
             weights[f"{net}_W{lay}"] = (rng.standard_normal((o, i)) * (weight_scale / np.sqrt(i))).astype(np.float32)
             weights[f"{net}_b{lay}"] = np.zeros((o,), np.float32)
+    if bias_scale != 0.0:   # drawn after all weights so that the default models are unchanged
+        for net in NETS:
+            for lay in ("1", "2", "3"):
+                b = weights[f"{net}_b{lay}"]
+                weights[f"{net}_b{lay}"] = (rng.standard_normal(b.shape) * bias_scale).astype(np.float32)
     return SDEModel(
         nu=nu, width=W, mass=v["mass"], gravity=g, k_thrust=v["mass"] * g / (nu * v["hover"] ** 2),
         inertia=np.asarray(v["inertia"], np.float32), mixer=_mixer(v["arm"], v["theta"], v["spin"], 0.016),

@@ -105,7 +105,10 @@ def test_cost_and_adjoint_vs_torch_autograd(vehicle, mode, P):
 
     import torch_ref
 
-    cfg, blob, model = make_setup(vehicle, mode, enu=False, num_particles=P)
+    cfg, _, _ = make_setup(vehicle, mode, enu=False, num_particles=P)
+    from sde4mbrl_px4_b200 import model_io
+    model = model_io.synthetic_model(vehicle, weight_scale=0.3, bias_scale=0.2)   # non-zero biases on every layer
+    blob = model.to_blob()
     o = O.Oracle(cfg, blob, "f64")
     pr, u, up = _problem(cfg, 1, 5)
     xi = np.random.default_rng(1).standard_normal((1, P, cfg.horizon, 6))
