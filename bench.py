@@ -315,6 +315,32 @@ def main():
                    "e2e": {"p50": pc(e2e_l, 50), "p99": pc(e2e_l, 99), "max": float(np.max(e2e_l))},
                    "device": {"p50": pc(dev_l, 50), "p99": pc(dev_l, 99), "max": float(np.max(dev_l))}}
 
+    # ---------------- tensor-core cost evaluation (supplementary: not the headline metric), rank 0 only ----------------
+    tensor_path = None
+    if rank == 0 and world == 1 and not args.no_latency:
+        from sde4mbrl_px4_b200 import config, synthetic
+
+        Bt = 65536
+        cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
+        cfg_tc = config.build_config(cfgd, convert_to_enu=True, tensor=True)
+        prt = synthetic.batched_problems(Bt, H, np.array(cfg.dt[:H]), seed=7)
+        ut = np.full((Bt, H, nu), 0.7, np.float32)
+        upt = ut[:, 0].copy()
+        res = {}
+        for name, c in (("fp32", cfg), ("tcgen05_tf32", cfg_tc)):
+            sr = solver.MPCSolver(c, blob, device=local)
+            ms = []
+            for _ in range(4):
+                Jr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=False)[0]
+                ms.append(sr.last_launch_ms())
+            res[name] = (float(np.median(ms[1:])), Jr)
+            sr.close()
+        tensor_path = {"workload": f"{Bt} forward rollouts x {H} steps (cost evaluation, sdempc_rollout, iris)",
+                       "fp32_ms": res["fp32"][0], "tcgen05_tf32_ms": res["tcgen05_tf32"][0],
+                       "tcgen05_rollouts_per_sec": Bt / res["tcgen05_tf32"][0] * 1e3,
+                       "fp32_rollouts_per_sec": Bt / res["fp32"][0] * 1e3,
+                       "max_rel_cost_error": float(np.max(np.abs(res["tcgen05_tf32"][1] - res["fp32"][1]) / np.abs(res["fp32"][1])))}
+
     # ---------------- roofline of the dominant (only) kernel ----------------
     ki = s.kernel_info()
     kernel_name = ("mpc_group_kernel<4,32,GP=4,GW=8>" if ki["problems_per_cta"] == 32 else
@@ -348,7 +374,7 @@ def main():
                     "ms_per_step": e2e_s / args.steps * 1e3},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline, "cpu_baseline": cb, "latency_ms": latency, "clocks": sampler.summary(),
-            "kernel_info": s.kernel_info(),
+            "kernel_info": s.kernel_info(), "tensor_path": tensor_path,
         }
         print(json.dumps(line))
     if dist is not None:

@@ -710,13 +710,14 @@ static void pack_weights(sdempc_handle* h) {
     }
 }
 
-// Operand image of the tensor-core path (TCLayout in mpc_tc.cuh): K-major rows of [W1 | b1], block-diagonal
-// [W2 | b2] and [W3 | b3] over the [drift | diffusion] hidden columns; the bias multiplies a constant-one input.
+// Operand image of the tensor-core path (TCLayout in mpc_tc.cuh): K-major rows of [W1 | b1] (b1 multiplies a
+// constant-one input), block-diagonal W2 and W3 over the [drift | diffusion] hidden columns, then b2 and b3.
 static void pack_weights_tc(sdempc_handle* h) {
     const int NU = h->mh.nu, W = h->mh.width, NIN = 6 + NU, N12 = 2 * W;
-    const int K1 = ((NIN + 1 + 7) / 8) * 8, K2 = N12 + 8, N3 = 16;
+    const int K1 = ((NIN + 1 + 7) / 8) * 8, K2 = N12, N3 = 16;
     const int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128;
-    const int B1 = 0, B2 = B1 + (N12 / 8) * SBO1, B3 = B2 + (N12 / 8) * SBO2, BYTES = B3 + (N3 / 8) * SBO2;
+    const int B1 = 0, B2 = B1 + (N12 / 8) * SBO1, B3 = B2 + (N12 / 8) * SBO2, BIAS2 = B3 + (N3 / 8) * SBO2, BIAS3 = BIAS2 + N12 * 4,
+              BYTES = BIAS3 + 16 * 4;
     auto off = [](int sbo, int row, int k) { return ((row / 8) * sbo + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4) / 4; };
     h->wimg_tc.assign(BYTES / 4, 0.f);
     float* I = h->wimg_tc.data();
@@ -731,14 +732,14 @@ static void pack_weights_tc(sdempc_handle* h) {
         for (int j = 0; j < W; ++j) {
             const int row = n * W + j;
             for (int k = 0; k < NIN; ++k) I[B1 / 4 + off(SBO1, row, k)] = W1[j * NIN + k];
-            I[B1 / 4 + off(SBO1, row, NIN)] = b1[j];
+            I[B1 / 4 + off(SBO1, row, NIN)] = b1[j];   // multiplies the constant-one input
             for (int k = 0; k < W; ++k) I[B2 / 4 + off(SBO2, row, n * W + k)] = W2[j * W + k];
-            I[B2 / 4 + off(SBO2, row, N12)] = b2[j];
+            I[BIAS2 / 4 + row] = b2[j];
         }
         for (int o = 0; o < 6; ++o) {
             const int row = n * 6 + o;
             for (int k = 0; k < W; ++k) I[B3 / 4 + off(SBO2, row, n * W + k)] = W3[o * W + k];
-            I[B3 / 4 + off(SBO2, row, N12)] = b3[o];
+            I[BIAS3 / 4 + row] = b3[o];
         }
     }
 }
