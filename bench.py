@@ -333,13 +333,21 @@ def main():
             for _ in range(4):
                 Jr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=False)[0]
                 ms.append(sr.last_launch_ms())
-            res[name] = (float(np.median(ms[1:])), Jr)
+            msg = []
+            for _ in range(3):
+                gr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=True)[1]
+                msg.append(sr.last_launch_ms())
+            res[name] = (float(np.median(ms[1:])), Jr, float(np.median(msg[1:])), gr)
             sr.close()
-        tensor_path = {"workload": f"{Bt} forward rollouts x {H} steps (cost evaluation, sdempc_rollout, iris)",
+        tensor_path = {"workload": f"{Bt} rollouts x {H} steps (sdempc_rollout: cost evaluation, and value_and_grad; iris)",
                        "fp32_ms": res["fp32"][0], "tcgen05_tf32_ms": res["tcgen05_tf32"][0],
                        "tcgen05_rollouts_per_sec": Bt / res["tcgen05_tf32"][0] * 1e3,
                        "fp32_rollouts_per_sec": Bt / res["fp32"][0] * 1e3,
-                       "max_rel_cost_error": float(np.max(np.abs(res["tcgen05_tf32"][1] - res["fp32"][1]) / np.abs(res["fp32"][1])))}
+                       "max_rel_cost_error": float(np.max(np.abs(res["tcgen05_tf32"][1] - res["fp32"][1]) / np.abs(res["fp32"][1]))),
+                       "value_and_grad": {"fp32_ms": res["fp32"][2], "tcgen05_tf32_ms": res["tcgen05_tf32"][2],
+                                          "max_grad_error_over_max_grad": float(np.max(
+                                              np.abs(res["tcgen05_tf32"][3] - res["fp32"][3]).reshape(Bt, -1).max(axis=1) /
+                                              np.abs(res["fp32"][3]).reshape(Bt, -1).max(axis=1)))}}
 
     # ---------------- roofline of the dominant (only) kernel ----------------
     ki = s.kernel_info()

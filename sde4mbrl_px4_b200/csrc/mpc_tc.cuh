@@ -31,7 +31,16 @@ struct TCLayout {
     static constexpr int B3 = B2 + (N12 / 8) * SBO2;
     static constexpr int BIAS2 = B3 + (N3 / 8) * SBO2;     // float b2[N12], then float b3[16]
     static constexpr int BIAS3 = BIAS2 + N12 * 4;
-    static constexpr int BYTES = BIAS3 + 16 * 4;
+    static constexpr int BYTES = BIAS3 + 16 * 4;           // forward image
+    // adjoint image (appended): transposed operands, no bias.  B3T [N12 rows x 16], B2T [N12 x N12], B1T [16 x N12]
+    static constexpr int SBO16 = (16 / 4) * 128;
+    static constexpr int B3T = BYTES;
+    static constexpr int B2T = B3T + (N12 / 8) * SBO16;
+    static constexpr int B1T = B2T + (N12 / 8) * SBO2;
+    static constexpr int BYTES_GRAD = B1T + (16 / 8) * SBO2;
+    // activation / step tape of the adjoint in global memory, float4 granules laid out [step][granule][row][4]:
+    // h1 (N12), h2 (N12), step tape (20: r6 sig6 dsg6 rn disc), noise (8), state x_t (16)
+    static constexpr int T_H1 = 0, T_H2 = N12 / 4, T_ST = 2 * N12 / 4, T_XI = T_ST + 5, T_X = T_XI + 2, TG = T_X + 4;
     // tensor-memory columns (fp32 each): D of layers 1-2 | A; the output layer's D reuses the first 16 columns
     static constexpr int C_D12 = 0, C_D3 = 0, C_A = N12;
     static constexpr int COLS = 2 * N12;                   // 128 or 256: a power of two >= 32
@@ -120,16 +129,17 @@ __device__ __forceinline__ void tc_ref_row(const KParams& P, int b, int t, float
 }
 
 // Body of the kernel (entry point in sdempc_api.cu).  wimg: TCLayout image in global memory.
-template <int NU, int W>
+template <int NU, int W, bool GRAD>
 __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char* sB, uint32_t* tmem_base_slot, uint64_t* bar) {
     using L = TCLayout<NU, W>;
     constexpr int NIN = L::NIN, N12 = L::N12;
+    constexpr int IMG = GRAD ? L::BYTES_GRAD : L::BYTES;
     const int tid = threadIdx.x, warp = tid >> 5;
     // ---- one-time setup: weights to shared memory, barrier, tensor memory ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(P.wimg);
         uint4* dst = reinterpret_cast<uint4*>(sB);
-        for (int i = tid; i < L::BYTES / 16; i += 128) dst[i] = __ldg(src + i);
+        for (int i = tid; i < IMG / 16; i += 128) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(bar)));
@@ -173,11 +183,20 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
     for (int i = 0; i < NU; ++i) up[i] = __ldg(P.uprev_in + (size_t)b * NU + i);
     const float* bias2 = reinterpret_cast<const float*>(sB + L::BIAS2);
     const float* bias3 = reinterpret_cast<const float*>(sB + L::BIAS3);
+    // this thread's float4 slot of tape granule g at step t: coalesced over the CTA's rows
+    float4* tape = reinterpret_cast<float4*>(P.mtape_g) + (size_t)blockIdx.x * P.H * L::TG * 128 + tid;
+    auto tp = [&](int t, int g) -> float4* { return tape + ((size_t)t * L::TG + g) * 128; };
     const unsigned long long seed = P.rng ? P.rng[2 * (size_t)b] : 0ull, tick = P.rng ? P.rng[2 * (size_t)b + 1] : 0ull;
     float Jp = 0.f, disc = 1.f;
     for (int t = 0; t < P.H; ++t) {
 #pragma unroll
         for (int i = 0; i < NU; ++i) u[i] = __ldg(P.u_in + ((size_t)b * P.H + t) * NU + i);
+        if constexpr (GRAD) {
+            *tp(t, L::T_X) = make_float4(x[0], x[1], x[2], x[3]);
+            *tp(t, L::T_X + 1) = make_float4(x[4], x[5], x[6], x[7]);
+            *tp(t, L::T_X + 2) = make_float4(x[8], x[9], x[10], x[11]);
+            *tp(t, L::T_X + 3) = make_float4(x[12], 0.f, 0.f, 0.f);
+        }
         // ---- layer 1 operand: [z, 1, 0 ...] ----
         {
             float z[NIN];
@@ -206,6 +225,10 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = tc::tanh_approx(v[i]);
             tc::st16(lane_addr + L::C_A + c0, v);
+            if constexpr (GRAD) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *tp(t, L::T_H1 + (c0 + i) / 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
         }
         tc::publish();
         if (tid == 0) {
@@ -226,6 +249,10 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
                 v[i + 2] = tc::tanh_approx(v[i + 2] + bv.z); v[i + 3] = tc::tanh_approx(v[i + 3] + bv.w);
             }
             tc::st16(lane_addr + L::C_A + c0, v);
+            if constexpr (GRAD) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *tp(t, L::T_H2 + (c0 + i) / 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
         }
         tc::publish();
         if (tid == 0) {
@@ -235,7 +262,7 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             tc::commit(bar);
         }
         tc::wait(bar, phase); phase ^= 1;
-        float r6[6], sig[6];
+        float r6[6], sig[6], dsg[6];
         {
             float o[16];
             tc::ld16(lane_addr + L::C_D3, o);
@@ -243,8 +270,9 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             for (int i = 0; i < 6; ++i) {
                 r6[i] = o[i] + bias3[i];
                 float sp, sg;
-                det_softplus_sigmoid_opt(o[6 + i] + bias3[6 + i], sp, sg, false);
+                det_softplus_sigmoid_opt(o[6 + i] + bias3[6 + i], sp, sg, GRAD);
                 sig[i] = P.sig0[i] * sp;
+                dsg[i] = P.sig0[i] * sg;
             }
         }
         // ---- noise, reference row, rigid body + Euler-Maruyama + cost ----
@@ -264,6 +292,15 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
         }
         tc_ref_row(P, b, t + 1, xr);
         const float l = phys_step<NU>(P, t, x, u, up, r6, sig, xi, xr, xn, rn);
+        if constexpr (GRAD) {
+            *tp(t, L::T_ST) = make_float4(r6[0], r6[1], r6[2], r6[3]);
+            *tp(t, L::T_ST + 1) = make_float4(r6[4], r6[5], sig[0], sig[1]);
+            *tp(t, L::T_ST + 2) = make_float4(sig[2], sig[3], sig[4], sig[5]);
+            *tp(t, L::T_ST + 3) = make_float4(dsg[0], dsg[1], dsg[2], dsg[3]);
+            *tp(t, L::T_ST + 4) = make_float4(dsg[4], dsg[5], rn, disc);
+            *tp(t, L::T_XI) = make_float4(xi[0], xi[1], xi[2], xi[3]);
+            *tp(t, L::T_XI + 1) = make_float4(xi[4], xi[5], 0.f, 0.f);
+        }
         Jp = fma_(disc, l, Jp);
         disc = disc * P.discount;
 #pragma unroll
@@ -285,6 +322,110 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
         }
     }
     if (valid) P.cost_out[b] = Jp;
+    if constexpr (GRAD) {
+        // ---- adjoint sweep: three transposed contractions per step (W3^T, W2^T, W1^T), tapes from global memory ----
+        const uint32_t id16 = tc::idesc_tf32(128, 16);
+        float lam[NX], gp[NU], xn[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { lam[i] = 0.f; xn[i] = x[i]; }   // x holds x_H after the forward loop
+#pragma unroll
+        for (int i = 0; i < NU; ++i) gp[i] = 0.f;
+        for (int t = P.H - 1; t >= 0; --t) {
+            float xt[NX];
+            {
+                const float4 a = *tp(t, L::T_X), c = *tp(t, L::T_X + 1), d = *tp(t, L::T_X + 2), e = *tp(t, L::T_X + 3);
+                xt[0] = a.x; xt[1] = a.y; xt[2] = a.z; xt[3] = a.w; xt[4] = c.x; xt[5] = c.y; xt[6] = c.z; xt[7] = c.w;
+                xt[8] = d.x; xt[9] = d.y; xt[10] = d.z; xt[11] = d.w; xt[12] = e.x;
+            }
+#pragma unroll
+            for (int i = 0; i < NU; ++i) u[i] = __ldg(P.u_in + ((size_t)b * P.H + t) * NU + i);
+#pragma unroll
+            for (int i = 0; i < NU; ++i)
+                up[i] = (t == 0) ? __ldg(P.uprev_in + (size_t)b * NU + i) : __ldg(P.u_in + ((size_t)b * P.H + t - 1) * NU + i);
+            BwdMid mid;
+            float gu[NU];
+            float2 lo[6];
+            {
+                float xr[NX], r012[3], sg6[6], dsg[6], xi[6], rn, dsc;
+                tc_ref_row(P, b, t + 1, xr);
+                const float4 a = *tp(t, L::T_ST), c = *tp(t, L::T_ST + 1), d = *tp(t, L::T_ST + 2), e = *tp(t, L::T_ST + 3),
+                             f = *tp(t, L::T_ST + 4), g0 = *tp(t, L::T_XI), g1 = *tp(t, L::T_XI + 1);
+                r012[0] = a.x; r012[1] = a.y; r012[2] = a.z;
+                sg6[0] = c.z; sg6[1] = c.w; sg6[2] = d.x; sg6[3] = d.y; sg6[4] = d.z; sg6[5] = d.w;
+                dsg[0] = e.x; dsg[1] = e.y; dsg[2] = e.z; dsg[3] = e.w; dsg[4] = f.x; dsg[5] = f.y;
+                rn = f.z; dsc = f.w;
+                xi[0] = g0.x; xi[1] = g0.y; xi[2] = g0.z; xi[3] = g0.w; xi[4] = g1.x; xi[5] = g1.y;
+                bwd_pre<NU>(P, t, xt, xn, xr, u, r012, sg6, dsg, rn, dsc, xi, lam, mid, lo, gu);
+            }
+            {   // output adjoints -> A[.., 16]: drift rows 0..5, diffusion rows 6..11
+                const float a[16] = {lo[0].x, lo[1].x, lo[2].x, lo[3].x, lo[4].x, lo[5].x, lo[0].y, lo[1].y,
+                                     lo[2].y, lo[3].y, lo[4].y, lo[5].y, 0.f, 0.f, 0.f, 0.f};
+                tc::st16(lane_addr + L::C_A, a);
+            }
+            tc::publish();
+            if (tid == 0) {
+#pragma unroll
+                for (int k8 = 0; k8 < 2; ++k8)
+                    tc::mma_ts(tb + L::C_D12, tb + L::C_A + 8 * k8, tc::desc(sb + L::B3T + k8 * 2 * L::LBO, L::SBO16), id12, k8 > 0);
+                tc::commit(bar);
+            }
+            tc::wait(bar, phase); phase ^= 1;
+#pragma unroll
+            for (int c0 = 0; c0 < N12; c0 += 16) {
+                float v[16];
+                tc::ld16(lane_addr + L::C_D12 + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 h = *tp(t, L::T_H2 + (c0 + i) / 4);
+                    v[i] = v[i] * fma_(-h.x, h.x, 1.f); v[i + 1] = v[i + 1] * fma_(-h.y, h.y, 1.f);
+                    v[i + 2] = v[i + 2] * fma_(-h.z, h.z, 1.f); v[i + 3] = v[i + 3] * fma_(-h.w, h.w, 1.f);
+                }
+                tc::st16(lane_addr + L::C_A + c0, v);
+            }
+            tc::publish();
+            if (tid == 0) {
+#pragma unroll
+                for (int k8 = 0; k8 < L::K2 / 8; ++k8)
+                    tc::mma_ts(tb + L::C_D12, tb + L::C_A + 8 * k8, tc::desc(sb + L::B2T + k8 * 2 * L::LBO, L::SBO2), id12, k8 > 0);
+                tc::commit(bar);
+            }
+            tc::wait(bar, phase); phase ^= 1;
+#pragma unroll
+            for (int c0 = 0; c0 < N12; c0 += 16) {
+                float v[16];
+                tc::ld16(lane_addr + L::C_D12 + c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 h = *tp(t, L::T_H1 + (c0 + i) / 4);
+                    v[i] = v[i] * fma_(-h.x, h.x, 1.f); v[i + 1] = v[i + 1] * fma_(-h.y, h.y, 1.f);
+                    v[i + 2] = v[i + 2] * fma_(-h.z, h.z, 1.f); v[i + 3] = v[i + 3] * fma_(-h.w, h.w, 1.f);
+                }
+                tc::st16(lane_addr + L::C_A + c0, v);
+            }
+            tc::publish();
+            if (tid == 0) {
+#pragma unroll
+                for (int k8 = 0; k8 < L::K2 / 8; ++k8)
+                    tc::mma_ts(tb + L::C_D3, tb + L::C_A + 8 * k8, tc::desc(sb + L::B1T + k8 * 2 * L::LBO, L::SBO2), id16, k8 > 0);
+                tc::commit(bar);
+            }
+            tc::wait(bar, phase); phase ^= 1;
+            float lz[NIN];
+            {
+                float o[16];
+                tc::ld16(lane_addr + L::C_D3, o);
+#pragma unroll
+                for (int i = 0; i < NIN; ++i) lz[i] = o[i];
+            }
+            bwd_post<NU>(P, xt, u, up, mid, lz, gu, gp, lam);
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < NU; ++i) P.grad_out[((size_t)b * P.H + t) * NU + i] = gu[i];
+            }
+#pragma unroll
+            for (int i = 0; i < NX; ++i) xn[i] = xt[i];
+        }
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"((uint32_t)L::COLS));

@@ -533,12 +533,12 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
 }
 
 // Tensor-core batched forward rollout (mpc_tc.cuh): 128 rollouts per CTA, thread = rollout = TMEM lane.  P = 1.
-template <int NU, int W>
+template <int NU, int W, bool GRAD>
 __global__ void __launch_bounds__(128, 1) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t tc_bar;
-    tc_rollout_body<NU, W>(P, tc_smem, &tmem_slot, &tc_bar);
+    tc_rollout_body<NU, W, GRAD>(P, tc_smem, &tmem_slot, &tc_bar);
 }
 
 // =====================================================================================
@@ -577,7 +577,8 @@ struct KernelChoice {
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (P == 1), SDEMPC_F_TENSOR
-    int tc_bytes;
+    void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
+    int tc_bytes, tc_bytes_grad, tc_tape_granules;
     int gp;
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
@@ -596,11 +597,14 @@ static KernelChoice make_choice() {
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     k.solve_pc = nullptr;
-    k.rollout_tc = nullptr;
-    k.tc_bytes = 0;
+    k.rollout_tc = k.rollout_tc_grad = nullptr;
+    k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = 0;
     if constexpr (PP == 1) {
-        k.rollout_tc = mpc_tc_rollout_kernel<NU, W>;
+        k.rollout_tc = mpc_tc_rollout_kernel<NU, W, false>;
+        k.rollout_tc_grad = mpc_tc_rollout_kernel<NU, W, true>;
         k.tc_bytes = TCLayout<NU, W>::BYTES;
+        k.tc_bytes_grad = TCLayout<NU, W>::BYTES_GRAD;
+        k.tc_tape_granules = TCLayout<NU, W>::TG;
     }
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
     k.gp = group_gp(NU, W);
@@ -644,8 +648,9 @@ struct sdempc_handle {
     KernelChoice kc;
     KParams kp;                       // template (config + model + layout)
     KParams kp_group;                 // same with the per-problem layout of the group kernel
-    std::vector<float> wimg_tc;       // tensor-core operand image (TCLayout)
+    std::vector<float> wimg_tc;       // tensor-core operand image (TCLayout), forward part then adjoint part
     float* d_wimg_tc = nullptr;
+    float* d_tape_tc = nullptr; size_t tape_tc_bytes = 0;
     size_t smem_bytes_group = 0;
     size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
@@ -719,7 +724,9 @@ static void pack_weights_tc(sdempc_handle* h) {
     const int B1 = 0, B2 = B1 + (N12 / 8) * SBO1, B3 = B2 + (N12 / 8) * SBO2, BIAS2 = B3 + (N3 / 8) * SBO2, BIAS3 = BIAS2 + N12 * 4,
               BYTES = BIAS3 + 16 * 4;
     auto off = [](int sbo, int row, int k) { return ((row / 8) * sbo + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4) / 4; };
-    h->wimg_tc.assign(BYTES / 4, 0.f);
+    const int SBO16 = (16 / 4) * 128, B3T = BYTES, B2T = B3T + (N12 / 8) * SBO16, B1T = B2T + (N12 / 8) * SBO2,
+              BYTES_GRAD = B1T + (16 / 8) * SBO2;
+    h->wimg_tc.assign(BYTES_GRAD / 4, 0.f);
     float* I = h->wimg_tc.data();
     const float* p = h->weights.data();
     for (int n = 0; n < 2; ++n) {
@@ -735,6 +742,10 @@ static void pack_weights_tc(sdempc_handle* h) {
             I[B1 / 4 + off(SBO1, row, NIN)] = b1[j];   // multiplies the constant-one input
             for (int k = 0; k < W; ++k) I[B2 / 4 + off(SBO2, row, n * W + k)] = W2[j * W + k];
             I[BIAS2 / 4 + row] = b2[j];
+            // adjoint operands: row = the hidden column that receives the adjoint
+            for (int o = 0; o < 6; ++o) I[B3T / 4 + off(SBO16, row, n * 6 + o)] = W3[o * W + j];          // (W3^T)[j][o]
+            for (int k = 0; k < W; ++k) I[B2T / 4 + off(SBO2, row, n * W + k)] = W2[k * W + j];           // (W2^T)[j][k]
+            for (int i = 0; i < NIN; ++i) I[B1T / 4 + off(SBO2, i, row)] = W1[j * NIN + i];               // (W1^T)[i][j]
         }
         for (int o = 0; o < 6; ++o) {
             const int row = n * 6 + o;
@@ -862,6 +873,7 @@ static int ensure_device(sdempc_handle* h) {
     }
     if (h->kc.rollout_tc) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_grad));
         CUDA_TRY(cudaMalloc(&h->d_wimg_tc, h->wimg_tc.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_wimg_tc, h->wimg_tc.data(), h->wimg_tc.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -907,7 +919,7 @@ static bool use_group(const sdempc_handle* h, int B) {
 static int ensure_mtape_group(sdempc_handle* h, int grid) {
     const size_t tapes = (size_t)grid * GROUP_GW * h->kc.gp;
     if (tapes <= h->mtape_group_n) return 0;
-    if (h->d_mtape_group) cudaFree(h->d_mtape_group); cudaFree(h->d_wimg_tc);
+    if (h->d_mtape_group) cudaFree(h->d_mtape_group); cudaFree(h->d_wimg_tc); cudaFree(h->d_tape_tc);
     h->d_mtape_group = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_mtape_group, tapes * (size_t)h->cfg.horizon * 2 * h->mh.width * sizeof(float2)));
     h->mtape_group_n = tapes;
@@ -1321,13 +1333,23 @@ int sdempc_rollout(sdempc_t* h, int B, const float* x, const float* curr_t, cons
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->cfg.flags & SDEMPC_F_TENSOR) {
         // tensor-core path: explicit opt-in, never a silent substitute (it is not SPEC-ARITH: TF32 products)
-        if (!h->kc.rollout_tc || P != 1 || grad != nullptr || h->cfg.u_slew_constr_coeff != 0.0f)
-            return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core rollout evaluates costs only (grad == NULL), with one particle and "
-                                       "no input-rate constraint");
+        if (!h->kc.rollout_tc || P != 1 || h->cfg.u_slew_constr_coeff != 0.0f)
+            return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core rollout supports one particle and no input-rate constraint");
         k.wimg = h->d_wimg_tc;
         const int tgrid = (B + 127) / 128;
+        if (grad) {   // activation / step tape of the adjoint: [CTA][step][granule][128 rows] float4
+            const size_t need = (size_t)tgrid * H * h->kc.tc_tape_granules * 128 * 16;
+            if (need > h->tape_tc_bytes) {
+                if (h->d_tape_tc) cudaFree(h->d_tape_tc);
+                h->d_tape_tc = nullptr; h->tape_tc_bytes = 0;
+                CUDA_TRY(cudaMalloc(&h->d_tape_tc, need));
+                h->tape_tc_bytes = need;
+            }
+            k.mtape_g = reinterpret_cast<float2*>(h->d_tape_tc);
+        }
         void* args[] = {&k};
-        CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(h->kc.rollout_tc), dim3(tgrid), dim3(128), args, (size_t)h->kc.tc_bytes, h->stream));
+        CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(grad ? h->kc.rollout_tc_grad : h->kc.rollout_tc), dim3(tgrid), dim3(128), args,
+                                  (size_t)(grad ? h->kc.tc_bytes_grad : h->kc.tc_bytes), h->stream));
         h->launches += 1;
         h->last_grid = tgrid;
     } else {

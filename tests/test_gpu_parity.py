@@ -245,11 +245,12 @@ def test_soft_slew_rate_constraint(solver, O, mode):
 
 @pytest.mark.parametrize("vehicle,scale,tol", [("iris", None, 1e-4), ("hexa", None, 1e-4), ("iris", 0.6, 5e-3)])
 def test_tensor_core_rollout_within_stated_tolerance(solver, O, vehicle, scale, tol):
-    """SDEMPC_F_TENSOR: the batched cost evaluation with the network layers on the tensor cores (tcgen05, TF32
+    """SDEMPC_F_TENSOR: the batched value_and_grad with the network layers on the tensor cores (tcgen05, TF32
     operands, fp32 accumulation, tanh.approx) is NOT bit-identical to SPEC-ARITH.  Stated bound: with the
-    BASELINE synthetic models the cost and the predicted trajectory stay within 1e-4 relative of the oracle
-    (north_star's FP32 bar; measured 2e-6); with networks six times larger in weight scale, where the learned
-    residual dominates the dynamics, within 5e-3 (the looser tensor-core bound)."""
+    BASELINE synthetic models the cost, the predicted trajectory and the gradient (relative to its largest
+    component) stay within 1e-4 of the oracle (north_star's FP32 bar; measured 2e-6 / 4e-6); with networks six
+    times larger in weight scale, where the learned residual dominates the dynamics, within 5e-3 (the looser
+    tensor-core bound)."""
     import os
 
     from conftest import ROOT
@@ -279,9 +280,18 @@ def test_tensor_core_rollout_within_stated_tolerance(solver, O, vehicle, scale, 
     Jt2 = s.rollout(pr["x"], u, up, xdes=xd, xi=xi, want_grad=False)[0]
     Jo2 = o.rollout(pr["x"], u, up, xdes=xd, xi=xi, want_grad=False)[0]
     assert np.max(np.abs(Jt2 - Jo2) / np.abs(Jo2)) <= tol
-    # it is an explicit opt-in with a narrow contract: gradients are refused, never silently served by another path
+    # value_and_grad: the adjoint sweep runs its three transposed contractions on the tensor cores as well
+    Jt3, gt3, _ = s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+    _, go, _ = o.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+    assert np.array_equal(Jt3, Jt)               # same forward arithmetic with and without the tape
+    gscale = np.abs(go).reshape(B, -1).max(axis=1)
+    assert np.max(np.abs(gt3 - go).reshape(B, -1).max(axis=1) / gscale) <= tol
+    # it is an explicit opt-in with a narrow contract: what it does not implement is refused, never silently
+    # served by another path
+    cfg_p = config.build_config(cfgd, tensor=True, num_particles=8 if vehicle == "iris" else 1)
+    cfg_p.u_slew_constr_coeff = 1.0
     with pytest.raises(RuntimeError, match="SDEMPC_F_TENSOR"):
-        s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+        solver.MPCSolver(cfg_p, blob).rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=False)
 
 
 @pytest.mark.parametrize("seed", list(range(24)))

@@ -39,6 +39,12 @@ rel = np.abs(Jt - Jf) / np.abs(Jf)
 print(f"B=300: cost rel err max {rel.max():.3e} median {np.median(rel):.3e}; x_evol max abs err {np.abs(xt - xf).max():.3e} "
       f"(|x| max {np.abs(xf).max():.2f}); J[0:3] fp32 {Jf[:3]} tensor {Jt[:3]}", flush=True)
 
+Jf, gf, _ = sf.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+Jt, gt, _ = st.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+gerr = np.abs(gt - gf).reshape(300, -1).max(axis=1) / np.abs(gf).reshape(300, -1).max(axis=1)
+print(f"B=300 value_and_grad: cost rel err max {(np.abs(Jt - Jf) / np.abs(Jf)).max():.3e}; gradient error / max|g| per problem: "
+      f"max {gerr.max():.3e} median {np.median(gerr):.3e}; g[0,0] fp32 {gf[0, 0]} tensor {gt[0, 0]}", flush=True)
+
 B = a.batch
 pr, u, up = problem(B, 7)
 for name, s in (("fp32", sf), ("tensor", st)):
@@ -49,3 +55,13 @@ for name, s in (("fp32", sf), ("tensor", st)):
     ms = np.array(ms[1:])
     print(f"{name}: B={B} forward rollouts (H={H}) {np.median(ms):.3f} ms -> {B / np.median(ms) * 1e3 / 1e6:.2f} M rollouts/s "
           f"(grid {s.kernel_info()['ctas']})", flush=True)
+
+Bg = min(B, 65536)
+pr, u, up = problem(Bg, 9)
+for name, s in (("fp32", sf), ("tensor", st)):
+    ms = []
+    for _ in range(3):
+        s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+        ms.append(s.last_launch_ms())
+    ms = np.array(ms[1:])
+    print(f"{name}: B={Bg} value_and_grad {np.median(ms):.3f} ms -> {Bg / np.median(ms) * 1e3 / 1e6:.2f} M/s", flush=True)
