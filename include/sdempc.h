@@ -59,7 +59,7 @@ extern "C" {
 #define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
 #define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
 #define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a 2-CTA cluster */
-#define SDEMPC_F_TENSOR 64u        /* sdempc_rollout (value_and_grad, P = 1): network layers and their adjoints on the tensor \
+#define SDEMPC_F_TENSOR 64u        /* sdempc_rollout (value_and_grad; 1, 2, 4 ... 32 particles): network layers and their adjoints on the tensor \
                                       cores (tcgen05, TF32 operands, fp32 accumulation, tanh.approx); NOT bit-identical to the \
                                       FP32 path: costs, trajectories and gradients agree within the tolerance stated in \
                                       DESIGN.md section 5 */

@@ -1,6 +1,7 @@
 // mpc_tc.cuh — tensor-core variant of the batched forward rollout (cost evaluation), tcgen05 + TMEM.
 //
-// Mapping: one CTA of 128 threads owns 128 rollouts; thread i is rollout (row) i and TMEM lane i.  The rigid
+// Mapping: one CTA of 128 threads owns 128 rollouts (rows = problems x particles; the particles of a problem are
+// adjacent lanes, their means are warp shuffles); thread i is rollout (row) i and TMEM lane i.  The rigid
 // body, the cost and the noise run per thread with the state in registers (every lane useful), and each network
 // layer is ONE dense contraction over the CTA's rows on the 5th-generation tensor cores:
 //     D[128 x N] (TMEM, fp32) = A[128 x K] (TMEM, written by the rows' own threads with tcgen05.st) * B[N x K]^T
@@ -159,9 +160,21 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
     const uint32_t id12 = tc::idesc_tf32(128, N12), id3 = tc::idesc_tf32(128, L::N3);
     uint32_t phase = 0;
 
-    const int row = blockIdx.x * 128 + tid;
-    const bool valid = row < P.B;
-    const int b = valid ? row : P.B - 1;   // rows past the batch shadow the last problem and store nothing
+    // row = problem * particles + particle: the particles of a problem are adjacent lanes of one warp (the
+    // particle count is a power of two <= 32), so the particle means are warp shuffles in particle order
+    const int pp = P.P, lane = tid & 31, pbase = lane & ~(pp - 1);
+    const int row = blockIdx.x * 128 + tid, nrows = P.B * pp;
+    const bool valid = row < nrows;
+    const int rr = valid ? row : nrows - 1;   // rows past the batch shadow the last row and store nothing
+    const int b = rr / pp, part = rr - b * pp;
+    const bool writer = valid && part == 0;
+    const float invP = __fdiv_rn(1.0f, (float)pp);
+    auto pmean = [&](float v) -> float {      // SPEC: sum over the particles in index order, times 1/P
+        if (pp == 1) return v;
+        float s = __shfl_sync(0xffffffffu, v, pbase);
+        for (int p = 1; p < pp; ++p) s = s + __shfl_sync(0xffffffffu, v, pbase + p);
+        return s * invP;
+    };
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
     float x[NX];
     {
@@ -174,7 +187,7 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             for (int i = 0; i < NX; ++i) x[i] = tmp[i];
         }
     }
-    if (valid && P.x_evol != nullptr) {
+    if (writer && P.x_evol != nullptr) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) P.x_evol[(size_t)b * (P.H + 1) * NX + i] = __ldg(P.x + (size_t)b * NX + i);
     }
@@ -279,15 +292,15 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
         float xi[6], xr[NX], xn[NX], rn;
         if (P.xi_override != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) xi[i] = __ldg(P.xi_override + ((size_t)b * P.H + t) * 6 + i);
+            for (int i = 0; i < 6; ++i) xi[i] = __ldg(P.xi_override + ((size_t)rr * P.H + t) * 6 + i);
         } else {
             const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
             const uint32_t c2 = (uint32_t)tick, c3 = ((uint32_t)(tick >> 32)) & 0x3FFFFFFFu;
             uint32_t r[4];
-            philox4x32_10((uint32_t)t, 0u, c2, c3, k0, k1, r);
+            philox4x32_10((uint32_t)t, (uint32_t)part, c2, c3, k0, k1, r);
             box_muller(r[0], r[1], xi[0], xi[1]);
             box_muller(r[2], r[3], xi[2], xi[3]);
-            philox4x32_10((uint32_t)t, 0u, c2, c3 | (1u << 30), k0, k1, r);
+            philox4x32_10((uint32_t)t, (uint32_t)part, c2, c3 | (1u << 30), k0, k1, r);
             box_muller(r[0], r[1], xi[4], xi[5]);
         }
         tc_ref_row(P, b, t + 1, xr);
@@ -307,21 +320,26 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
         for (int i = 0; i < NU; ++i) up[i] = u[i];
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = xn[i];
-        if (valid && P.x_evol != nullptr) {
+        if (P.x_evol != nullptr) {            // predicted mean trajectory: particle mean, quaternion renormalised
             float rowv[NX], o[NX];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) rowv[i] = xn[i];
+            for (int i = 0; i < NX; ++i) rowv[i] = pmean(xn[i]);
             quat_renorm(rowv + 6);
             if (enu) enu_ned(rowv, o);
             else {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) o[i] = rowv[i];
             }
+            if (writer) {
 #pragma unroll
-            for (int i = 0; i < NX; ++i) P.x_evol[((size_t)b * (P.H + 1) + t + 1) * NX + i] = o[i];
+                for (int i = 0; i < NX; ++i) P.x_evol[((size_t)b * (P.H + 1) + t + 1) * NX + i] = o[i];
+            }
         }
     }
-    if (valid) P.cost_out[b] = Jp;
+    {
+        const float Jm = pmean(Jp);
+        if (writer) P.cost_out[b] = Jm;
+    }
     if constexpr (GRAD) {
         // ---- adjoint sweep: three transposed contractions per step (W3^T, W2^T, W1^T), tapes from global memory ----
         const uint32_t id16 = tc::idesc_tf32(128, 16);
@@ -418,9 +436,10 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
                 for (int i = 0; i < NIN; ++i) lz[i] = o[i];
             }
             bwd_post<NU>(P, xt, u, up, mid, lz, gu, gp, lam);
-            if (valid) {
 #pragma unroll
-                for (int i = 0; i < NU; ++i) P.grad_out[((size_t)b * P.H + t) * NU + i] = gu[i];
+            for (int i = 0; i < NU; ++i) {
+                const float gm = pmean(gu[i]);
+                if (writer) P.grad_out[((size_t)b * P.H + t) * NU + i] = gm;
             }
 #pragma unroll
             for (int i = 0; i < NX; ++i) xn[i] = xt[i];

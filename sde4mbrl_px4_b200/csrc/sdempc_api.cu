@@ -532,7 +532,7 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
     }
 }
 
-// Tensor-core batched forward rollout (mpc_tc.cuh): 128 rollouts per CTA, thread = rollout = TMEM lane.  P = 1.
+// Tensor-core batched rollout / value_and_grad (mpc_tc.cuh): 128 rows per CTA, thread = (problem, particle) = TMEM lane.
 template <int NU, int W, bool GRAD>
 __global__ void __launch_bounds__(128, 1) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
@@ -576,7 +576,7 @@ struct KernelChoice {
     void (*closed_cl)(KParams);
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
-    void (*rollout_tc)(KParams);   // tensor-core forward rollout (P == 1), SDEMPC_F_TENSOR
+    void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
     int tc_bytes, tc_bytes_grad, tc_tape_granules;
     int gp;
@@ -599,7 +599,7 @@ static KernelChoice make_choice() {
     k.solve_pc = nullptr;
     k.rollout_tc = k.rollout_tc_grad = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = 0;
-    if constexpr (PP == 1) {
+    {   // one tensor-core kernel per (nu, width): the particle count is a run-time row mapping
         k.rollout_tc = mpc_tc_rollout_kernel<NU, W, false>;
         k.rollout_tc_grad = mpc_tc_rollout_kernel<NU, W, true>;
         k.tc_bytes = TCLayout<NU, W>::BYTES;
@@ -1333,10 +1333,11 @@ int sdempc_rollout(sdempc_t* h, int B, const float* x, const float* curr_t, cons
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if (h->cfg.flags & SDEMPC_F_TENSOR) {
         // tensor-core path: explicit opt-in, never a silent substitute (it is not SPEC-ARITH: TF32 products)
-        if (!h->kc.rollout_tc || P != 1 || h->cfg.u_slew_constr_coeff != 0.0f)
-            return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core rollout supports one particle and no input-rate constraint");
+        // rows = problems x particles; the particles of a problem are adjacent lanes of one warp
+        if (!h->kc.rollout_tc || P > 32 || (P & (P - 1)) != 0 || h->cfg.u_slew_constr_coeff != 0.0f)
+            return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core rollout supports 1, 2, 4, ... 32 particles and no input-rate constraint");
         k.wimg = h->d_wimg_tc;
-        const int tgrid = (B + 127) / 128;
+        const int tgrid = (int)(((size_t)B * P + 127) / 128);
         if (grad) {   // activation / step tape of the adjoint: [CTA][step][granule][128 rows] float4
             const size_t need = (size_t)tgrid * H * h->kc.tc_tape_granules * 128 * 16;
             if (need > h->tape_tc_bytes) {

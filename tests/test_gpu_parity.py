@@ -288,10 +288,48 @@ def test_tensor_core_rollout_within_stated_tolerance(solver, O, vehicle, scale, 
     assert np.max(np.abs(gt3 - go).reshape(B, -1).max(axis=1) / gscale) <= tol
     # it is an explicit opt-in with a narrow contract: what it does not implement is refused, never silently
     # served by another path
-    cfg_p = config.build_config(cfgd, tensor=True, num_particles=8 if vehicle == "iris" else 1)
+    cfg_p = config.build_config(cfgd, tensor=True)
     cfg_p.u_slew_constr_coeff = 1.0
     with pytest.raises(RuntimeError, match="SDEMPC_F_TENSOR"):
         solver.MPCSolver(cfg_p, blob).rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=False)
+
+
+@pytest.mark.parametrize("vehicle,particles", [("hexa", 8), ("iris", 8), ("iris", 2)])
+def test_tensor_core_rollout_with_particles(solver, O, vehicle, particles):
+    """BASELINE config 3 shape (hexa, 8 particles) on the tensor-core path: rows = problems x particles, the
+    particles of a problem are adjacent TMEM lanes, and the particle means of the cost, the gradient and the
+    predicted trajectory are warp shuffles in particle order.  Same stated bound as the one-particle case (1e-4
+    relative with the BASELINE synthetic models); Philox noise per (step, particle) and an explicit noise tensor
+    both go through the kernel."""
+    import os
+
+    from conftest import ROOT
+    from sde4mbrl_px4_b200 import config, model_io
+
+    cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{vehicle}_traj.yaml"))
+    cfg_t = config.build_config(cfgd, tensor=True, num_particles=particles)
+    cfg_f = config.build_config(cfgd, num_particles=particles)
+    blob = model_io.synthetic_model(vehicle, bias_scale=0.05).to_blob()
+    s, o = solver.MPCSolver(cfg_t, blob), O.Oracle(cfg_f, blob, "f32")
+    B, H, nu, tol = 77, cfg_f.horizon, cfg_f.nu, 1e-4   # 77 x 8 rows: not a multiple of the 128 rows of a CTA
+    pr = synthetic.batched_problems(B, H, np.array(cfg_f.dt[:H]), seed=33)
+    rng = np.random.default_rng(8)
+    u = np.clip(np.array(cfg_f.uref[:nu]) + 0.05 * rng.standard_normal((B, H, nu)), 1e-4, 1).astype(np.float32)
+    up = np.tile(np.array(cfg_f.uref[:nu], np.float32), (B, 1))
+    Jt, gt, xt = s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+    Jo, go, xo = o.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
+    assert np.all(np.isfinite(Jt)) and np.max(np.abs(Jt - Jo) / np.abs(Jo)) <= tol
+    assert np.abs(xt - xo).max() <= tol * np.abs(xo).max()
+    gscale = np.abs(go).reshape(B, -1).max(axis=1)
+    assert np.max(np.abs(gt - go).reshape(B, -1).max(axis=1) / gscale) <= tol
+    # the particles see different noise: the mean differs from the one-particle evaluation of the same problems
+    o1 = O.Oracle(config.build_config(cfgd), blob, "f32")
+    J1 = o1.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=False)[0]
+    assert np.max(np.abs(J1 - Jo) / np.abs(Jo)) > 10 * tol
+    xi = np.random.default_rng(6).standard_normal((B, particles, H, 6)).astype(np.float32)
+    Jt2 = s.rollout(pr["x"], u, up, xref_win=pr["xref_win"], xi=xi, want_grad=False)[0]
+    Jo2 = o.rollout(pr["x"], u, up, xref_win=pr["xref_win"], xi=xi, want_grad=False)[0]
+    assert np.max(np.abs(Jt2 - Jo2) / np.abs(Jo2)) <= tol
 
 
 @pytest.mark.parametrize("seed", list(range(24)))

@@ -15,11 +15,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=65536)
 ap.add_argument("--vehicle", default="iris")
 ap.add_argument("--lib", default=None)
+ap.add_argument("--particles", type=int, default=1)
 a = ap.parse_args()
 cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{a.vehicle}_traj.yaml"))
 blob = model_io.synthetic_model(a.vehicle).to_blob()
-cfg_f = config.build_config(cfgd, convert_to_enu=True)
-cfg_t = config.build_config(cfgd, convert_to_enu=True, tensor=True)
+cfg_f = config.build_config(cfgd, convert_to_enu=True, num_particles=a.particles)
+cfg_t = config.build_config(cfgd, convert_to_enu=True, tensor=True, num_particles=a.particles)
 sf, st = solver.MPCSolver(cfg_f, blob, lib_path=a.lib), solver.MPCSolver(cfg_t, blob, lib_path=a.lib)
 H, nu = cfg_f.horizon, cfg_f.nu
 
@@ -36,7 +37,7 @@ pr, u, up = problem(300, 5)
 Jf, _, xf = sf.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=False)
 Jt, _, xt = st.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=False)
 rel = np.abs(Jt - Jf) / np.abs(Jf)
-print(f"B=300: cost rel err max {rel.max():.3e} median {np.median(rel):.3e}; x_evol max abs err {np.abs(xt - xf).max():.3e} "
+print(f"particles {a.particles}; B=300: cost rel err max {rel.max():.3e} median {np.median(rel):.3e}; x_evol max abs err {np.abs(xt - xf).max():.3e} "
       f"(|x| max {np.abs(xf).max():.2f}); J[0:3] fp32 {Jf[:3]} tensor {Jt[:3]}", flush=True)
 
 Jf, gf, _ = sf.rollout(pr["x"], u, up, xref_win=pr["xref_win"], rng=pr["rng"], want_grad=True)
