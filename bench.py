@@ -318,36 +318,45 @@ def main():
     # ---------------- tensor-core cost evaluation (supplementary: not the headline metric), rank 0 only ----------------
     tensor_path = None
     if rank == 0 and world == 1 and not args.no_latency:
-        from sde4mbrl_px4_b200 import config, synthetic
+        from sde4mbrl_px4_b200 import config, model_io, synthetic
 
-        Bt = 65536
-        cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
-        cfg_tc = config.build_config(cfgd, convert_to_enu=True, tensor=True)
-        prt = synthetic.batched_problems(Bt, H, np.array(cfg.dt[:H]), seed=7)
-        ut = np.full((Bt, H, nu), 0.7, np.float32)
-        upt = ut[:, 0].copy()
-        res = {}
-        for name, c in (("fp32", cfg), ("tcgen05_tf32", cfg_tc)):
-            sr = solver.MPCSolver(c, blob, device=local)
-            ms = []
-            for _ in range(4):
-                Jr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=False)[0]
-                ms.append(sr.last_launch_ms())
-            msg = []
-            for _ in range(3):
-                gr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=True)[1]
-                msg.append(sr.last_launch_ms())
-            res[name] = (float(np.median(ms[1:])), Jr, float(np.median(msg[1:])), gr)
-            sr.close()
-        tensor_path = {"workload": f"{Bt} rollouts x {H} steps (sdempc_rollout: cost evaluation, and value_and_grad; iris)",
-                       "fp32_ms": res["fp32"][0], "tcgen05_tf32_ms": res["tcgen05_tf32"][0],
-                       "tcgen05_rollouts_per_sec": Bt / res["tcgen05_tf32"][0] * 1e3,
-                       "fp32_rollouts_per_sec": Bt / res["fp32"][0] * 1e3,
-                       "max_rel_cost_error": float(np.max(np.abs(res["tcgen05_tf32"][1] - res["fp32"][1]) / np.abs(res["fp32"][1]))),
-                       "value_and_grad": {"fp32_ms": res["fp32"][2], "tcgen05_tf32_ms": res["tcgen05_tf32"][2],
-                                          "max_grad_error_over_max_grad": float(np.max(
-                                              np.abs(res["tcgen05_tf32"][3] - res["fp32"][3]).reshape(Bt, -1).max(axis=1) /
-                                              np.abs(res["fp32"][3]).reshape(Bt, -1).max(axis=1)))}}
+        def tc_pair(vehicle, particles, Bt):
+            """sdempc_rollout on the FP32 path and on the tcgen05 path, same inputs: launch times and differences."""
+            cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{vehicle}_traj.yaml"))
+            blob_v = model_io.synthetic_model(vehicle).to_blob()
+            cfgs = {"fp32": config.build_config(cfgd, convert_to_enu=True, num_particles=particles),
+                    "tcgen05_tf32": config.build_config(cfgd, convert_to_enu=True, num_particles=particles, tensor=True)}
+            Hv, nuv = cfgs["fp32"].horizon, cfgs["fp32"].nu
+            prt = synthetic.batched_problems(Bt, Hv, np.array(cfgs["fp32"].dt[:Hv]), seed=7)
+            ut = np.full((Bt, Hv, nuv), float(cfgs["fp32"].uref[0]), np.float32)
+            upt = ut[:, 0].copy()
+            res = {}
+            for name, c in cfgs.items():
+                sr = solver.MPCSolver(c, blob_v, device=local)
+                ms = []
+                for _ in range(4):
+                    Jr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=False)[0]
+                    ms.append(sr.last_launch_ms())
+                msg = []
+                for _ in range(3):
+                    gr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=True)[1]
+                    msg.append(sr.last_launch_ms())
+                res[name] = (float(np.median(ms[1:])), Jr, float(np.median(msg[1:])), gr)
+                sr.close()
+            f, t = res["fp32"], res["tcgen05_tf32"]
+            rows = Bt * particles
+            return {"workload": f"{Bt} problems x {particles} particle(s) x {Hv} steps (sdempc_rollout: cost evaluation, and "
+                                f"value_and_grad; {vehicle})",
+                    "fp32_ms": f[0], "tcgen05_tf32_ms": t[0], "tcgen05_rollouts_per_sec": rows / t[0] * 1e3,
+                    "fp32_rollouts_per_sec": rows / f[0] * 1e3,
+                    "max_rel_cost_error": float(np.max(np.abs(t[1] - f[1]) / np.abs(f[1]))),
+                    "value_and_grad": {"fp32_ms": f[2], "tcgen05_tf32_ms": t[2],
+                                       "max_grad_error_over_max_grad": float(np.max(
+                                           np.abs(t[3] - f[3]).reshape(Bt, -1).max(axis=1) / np.abs(f[3]).reshape(Bt, -1).max(axis=1)))}}
+
+        tensor_path = tc_pair("iris", 1, 65536)
+        # BASELINE config 3 shape (hexacopter, 8 particles) as a batch: the same 65 536 rows
+        tensor_path["hexa_8_particles"] = tc_pair("hexa", 8, 8192)
 
     # ---------------- roofline of the dominant (only) kernel ----------------
     ki = s.kernel_info()

@@ -14,6 +14,7 @@
 // Per step: st(z) -> MMA -> ld/tanh/st -> MMA -> ld/tanh/st -> MMA -> ld -> softplus, rigid body, cost.
 // tools/tc_probe.cu is the isolated check of the descriptor / TMEM conventions used here.
 #pragma once
+#include <cuda_fp16.h>
 #include "mpc_kernels.cuh"
 
 namespace sdempc {
@@ -39,9 +40,12 @@ struct TCLayout {
     static constexpr int B2T = B3T + (N12 / 8) * SBO16;
     static constexpr int B1T = B2T + (N12 / 8) * SBO2;
     static constexpr int BYTES_GRAD = B1T + (16 / 8) * SBO2;
-    // activation / step tape of the adjoint in global memory, float4 granules laid out [step][granule][row][4]:
-    // h1 (N12), h2 (N12), step tape (20: r6 sig6 dsg6 rn disc), noise (8), state x_t (16)
-    static constexpr int T_H1 = 0, T_H2 = N12 / 4, T_ST = 2 * N12 / 4, T_XI = T_ST + 5, T_X = T_XI + 2, TG = T_X + 4;
+    // activation / step tape of the adjoint in global memory, 16-byte granules laid out [step][granule][row]:
+    // h1 (N12 halves), h2 (N12 halves), then 9 granules of floats: what the sweep reads of the step tape (r[0..2],
+    // sig6, dsg6, 1/|q|, discount^t), the noise (6) and the state x_t (13).
+    // The hidden activations are kept as fp16: 10 mantissa bits, what the next layer's TF32 operand read keeps of
+    // them anyway (|h| <= 1, so the range is no issue); this is 37 % less tape traffic for the HBM-bound sweep.
+    static constexpr int T_H1 = 0, T_H2 = N12 / 8, T_ST = 2 * N12 / 8, TG = T_ST + 9;
     // tensor-memory columns (fp32 each): D of layers 1-2 | A; the output layer's D reuses the first 16 columns
     static constexpr int C_D12 = 0, C_D3 = 0, C_A = N12;
     static constexpr int COLS = 2 * N12;                   // 128 or 256: a power of two >= 32
@@ -101,6 +105,23 @@ __device__ __forceinline__ void publish() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// eight activations <-> one 16-byte tape granule of fp16 pairs
+__device__ __forceinline__ float4 pack8(const float* v) {
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]), c = __floats2half2_rn(v[4], v[5]),
+                  d = __floats2half2_rn(v[6], v[7]);
+    float4 o;
+    o.x = __uint_as_float(*reinterpret_cast<const uint32_t*>(&a)); o.y = __uint_as_float(*reinterpret_cast<const uint32_t*>(&b));
+    o.z = __uint_as_float(*reinterpret_cast<const uint32_t*>(&c)); o.w = __uint_as_float(*reinterpret_cast<const uint32_t*>(&d));
+    return o;
+}
+__device__ __forceinline__ void unpack8(const float4 g, float (&h)[8]) {
+    const uint32_t w[4] = {__float_as_uint(g.x), __float_as_uint(g.y), __float_as_uint(g.z), __float_as_uint(g.w)};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        h[2 * i] = f.x; h[2 * i + 1] = f.y;
+    }
 }
 __device__ __forceinline__ float tanh_approx(float x) {
     float y;
@@ -204,12 +225,6 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
     for (int t = 0; t < P.H; ++t) {
 #pragma unroll
         for (int i = 0; i < NU; ++i) u[i] = __ldg(P.u_in + ((size_t)b * P.H + t) * NU + i);
-        if constexpr (GRAD) {
-            *tp(t, L::T_X) = make_float4(x[0], x[1], x[2], x[3]);
-            *tp(t, L::T_X + 1) = make_float4(x[4], x[5], x[6], x[7]);
-            *tp(t, L::T_X + 2) = make_float4(x[8], x[9], x[10], x[11]);
-            *tp(t, L::T_X + 3) = make_float4(x[12], 0.f, 0.f, 0.f);
-        }
         // ---- layer 1 operand: [z, 1, 0 ...] ----
         {
             float z[NIN];
@@ -239,8 +254,8 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             for (int i = 0; i < 16; ++i) v[i] = tc::tanh_approx(v[i]);
             tc::st16(lane_addr + L::C_A + c0, v);
             if constexpr (GRAD) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) *tp(t, L::T_H1 + (c0 + i) / 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                *tp(t, L::T_H1 + c0 / 8) = tc::pack8(v);
+                *tp(t, L::T_H1 + c0 / 8 + 1) = tc::pack8(v + 8);
             }
         }
         tc::publish();
@@ -263,8 +278,8 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             }
             tc::st16(lane_addr + L::C_A + c0, v);
             if constexpr (GRAD) {
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) *tp(t, L::T_H2 + (c0 + i) / 4) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                *tp(t, L::T_H2 + c0 / 8) = tc::pack8(v);
+                *tp(t, L::T_H2 + c0 / 8 + 1) = tc::pack8(v + 8);
             }
         }
         tc::publish();
@@ -306,13 +321,15 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
         tc_ref_row(P, b, t + 1, xr);
         const float l = phys_step<NU>(P, t, x, u, up, r6, sig, xi, xr, xn, rn);
         if constexpr (GRAD) {
-            *tp(t, L::T_ST) = make_float4(r6[0], r6[1], r6[2], r6[3]);
-            *tp(t, L::T_ST + 1) = make_float4(r6[4], r6[5], sig[0], sig[1]);
-            *tp(t, L::T_ST + 2) = make_float4(sig[2], sig[3], sig[4], sig[5]);
-            *tp(t, L::T_ST + 3) = make_float4(dsg[0], dsg[1], dsg[2], dsg[3]);
-            *tp(t, L::T_ST + 4) = make_float4(dsg[4], dsg[5], rn, disc);
-            *tp(t, L::T_XI) = make_float4(xi[0], xi[1], xi[2], xi[3]);
-            *tp(t, L::T_XI + 1) = make_float4(xi[4], xi[5], 0.f, 0.f);
+            *tp(t, L::T_ST) = make_float4(r6[0], r6[1], r6[2], sig[0]);
+            *tp(t, L::T_ST + 1) = make_float4(sig[1], sig[2], sig[3], sig[4]);
+            *tp(t, L::T_ST + 2) = make_float4(sig[5], dsg[0], dsg[1], dsg[2]);
+            *tp(t, L::T_ST + 3) = make_float4(dsg[3], dsg[4], dsg[5], rn);
+            *tp(t, L::T_ST + 4) = make_float4(disc, xi[0], xi[1], xi[2]);
+            *tp(t, L::T_ST + 5) = make_float4(xi[3], xi[4], xi[5], x[0]);      // x is still x_t here
+            *tp(t, L::T_ST + 6) = make_float4(x[1], x[2], x[3], x[4]);
+            *tp(t, L::T_ST + 7) = make_float4(x[5], x[6], x[7], x[8]);
+            *tp(t, L::T_ST + 8) = make_float4(x[9], x[10], x[11], x[12]);
         }
         Jp = fma_(disc, l, Jp);
         disc = disc * P.discount;
@@ -349,11 +366,14 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
 #pragma unroll
         for (int i = 0; i < NU; ++i) gp[i] = 0.f;
         for (int t = P.H - 1; t >= 0; --t) {
-            float xt[NX];
+            float xt[NX], xi[6];
+            const float4 s0 = *tp(t, L::T_ST), s1 = *tp(t, L::T_ST + 1), s2 = *tp(t, L::T_ST + 2), s3 = *tp(t, L::T_ST + 3),
+                         s4 = *tp(t, L::T_ST + 4);
             {
-                const float4 a = *tp(t, L::T_X), c = *tp(t, L::T_X + 1), d = *tp(t, L::T_X + 2), e = *tp(t, L::T_X + 3);
-                xt[0] = a.x; xt[1] = a.y; xt[2] = a.z; xt[3] = a.w; xt[4] = c.x; xt[5] = c.y; xt[6] = c.z; xt[7] = c.w;
-                xt[8] = d.x; xt[9] = d.y; xt[10] = d.z; xt[11] = d.w; xt[12] = e.x;
+                const float4 a = *tp(t, L::T_ST + 5), c = *tp(t, L::T_ST + 6), d = *tp(t, L::T_ST + 7), e = *tp(t, L::T_ST + 8);
+                xi[0] = s4.y; xi[1] = s4.z; xi[2] = s4.w; xi[3] = a.x; xi[4] = a.y; xi[5] = a.z;
+                xt[0] = a.w; xt[1] = c.x; xt[2] = c.y; xt[3] = c.z; xt[4] = c.w; xt[5] = d.x; xt[6] = d.y; xt[7] = d.z; xt[8] = d.w;
+                xt[9] = e.x; xt[10] = e.y; xt[11] = e.z; xt[12] = e.w;
             }
 #pragma unroll
             for (int i = 0; i < NU; ++i) u[i] = __ldg(P.u_in + ((size_t)b * P.H + t) * NU + i);
@@ -364,15 +384,12 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             float gu[NU];
             float2 lo[6];
             {
-                float xr[NX], r012[3], sg6[6], dsg[6], xi[6], rn, dsc;
+                float xr[NX];
                 tc_ref_row(P, b, t + 1, xr);
-                const float4 a = *tp(t, L::T_ST), c = *tp(t, L::T_ST + 1), d = *tp(t, L::T_ST + 2), e = *tp(t, L::T_ST + 3),
-                             f = *tp(t, L::T_ST + 4), g0 = *tp(t, L::T_XI), g1 = *tp(t, L::T_XI + 1);
-                r012[0] = a.x; r012[1] = a.y; r012[2] = a.z;
-                sg6[0] = c.z; sg6[1] = c.w; sg6[2] = d.x; sg6[3] = d.y; sg6[4] = d.z; sg6[5] = d.w;
-                dsg[0] = e.x; dsg[1] = e.y; dsg[2] = e.z; dsg[3] = e.w; dsg[4] = f.x; dsg[5] = f.y;
-                rn = f.z; dsc = f.w;
-                xi[0] = g0.x; xi[1] = g0.y; xi[2] = g0.z; xi[3] = g0.w; xi[4] = g1.x; xi[5] = g1.y;
+                const float r012[3] = {s0.x, s0.y, s0.z};
+                const float sg6[6] = {s0.w, s1.x, s1.y, s1.z, s1.w, s2.x};
+                const float dsg[6] = {s2.y, s2.z, s2.w, s3.x, s3.y, s3.z};
+                const float rn = s3.w, dsc = s4.x;
                 bwd_pre<NU>(P, t, xt, xn, xr, u, r012, sg6, dsg, rn, dsc, xi, lam, mid, lo, gu);
             }
             {   // output adjoints -> A[.., 16]: drift rows 0..5, diffusion rows 6..11
@@ -393,10 +410,11 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
                 float v[16];
                 tc::ld16(lane_addr + L::C_D12 + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 h = *tp(t, L::T_H2 + (c0 + i) / 4);
-                    v[i] = v[i] * fma_(-h.x, h.x, 1.f); v[i + 1] = v[i + 1] * fma_(-h.y, h.y, 1.f);
-                    v[i + 2] = v[i + 2] * fma_(-h.z, h.z, 1.f); v[i + 3] = v[i + 3] * fma_(-h.w, h.w, 1.f);
+                for (int i = 0; i < 16; i += 8) {
+                    float h[8];
+                    tc::unpack8(*tp(t, L::T_H2 + (c0 + i) / 8), h);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) v[i + m] = v[i + m] * fma_(-h[m], h[m], 1.f);
                 }
                 tc::st16(lane_addr + L::C_A + c0, v);
             }
@@ -413,10 +431,11 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
                 float v[16];
                 tc::ld16(lane_addr + L::C_D12 + c0, v);
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    const float4 h = *tp(t, L::T_H1 + (c0 + i) / 4);
-                    v[i] = v[i] * fma_(-h.x, h.x, 1.f); v[i + 1] = v[i + 1] * fma_(-h.y, h.y, 1.f);
-                    v[i + 2] = v[i + 2] * fma_(-h.z, h.z, 1.f); v[i + 3] = v[i + 3] * fma_(-h.w, h.w, 1.f);
+                for (int i = 0; i < 16; i += 8) {
+                    float h[8];
+                    tc::unpack8(*tp(t, L::T_H1 + (c0 + i) / 8), h);
+#pragma unroll
+                    for (int m = 0; m < 8; ++m) v[i + m] = v[i + m] * fma_(-h[m], h[m], 1.f);
                 }
                 tc::st16(lane_addr + L::C_A + c0, v);
             }

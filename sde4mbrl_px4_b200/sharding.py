@@ -110,3 +110,37 @@ def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
     for k, (off, shape) in layout.items():
         res[k] = bufs[k][1].numpy().reshape((world * shape[0],) + tuple(shape[1:]))
     return res
+
+
+def closed_loop_sharded(solver, x0, t0, rng, ticks: int, device=None) -> dict | None:
+    """Monte-Carlo closed loop (BASELINE config 5) over all ranks: every rank is given the same global
+    ``x0[R,13]``, ``t0[R]``, ``rng[R,2]``, takes its contiguous block of rollouts, runs the whole ``ticks``-tick
+    loop of plant + MPC on its GPU in ONE launch (no host synchronisation and no collective inside the loop), and
+    the only exchange is at the end: the per-rollout statistics ``[R,4]`` = (rms position error, max position
+    error, mean opt_cost, mean num_steps) are gathered on rank 0 and the device time is reduced with MAX.
+    Returns on rank 0 ``{"stats", "device_s", "ticks_per_s", "rollouts_per_s", "rollouts_per_rank"}``, else None."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    x0 = np.ascontiguousarray(x0, np.float32).reshape(-1, 13)
+    R = x0.shape[0]
+    lo, hi = shard_range(R, rank, world)
+    t0 = np.ascontiguousarray(t0, np.float32).reshape(R)
+    rng = np.ascontiguousarray(rng, np.uint64).reshape(R, 2)
+    if hi > lo:
+        _, _, st = solver.closed_loop(x0[lo:hi], t0[lo:hi], rng[lo:hi], ticks, want_hist=False)
+        ms = float(solver.last_launch_ms())
+    else:                                    # more ranks than rollouts: this rank only takes part in the exchange
+        st, ms = np.zeros((0, 4), np.float32), 0.0
+    tms = torch.tensor([ms], dtype=torch.float32)
+    if device is not None:
+        tms = tms.to(device)
+    dist.all_reduce(tms, op=dist.ReduceOp.MAX)       # multi-GPU time = the slowest rank's device time
+    res = gather_results({"stats": st}, R, device=device)
+    if rank != 0:
+        return None
+    dev_s = float(tms.item()) * 1e-3
+    return {"stats": res["stats"], "device_s": dev_s, "ticks_per_s": R * ticks / dev_s if dev_s > 0 else float("nan"),
+            "rollouts_per_s": R / dev_s if dev_s > 0 else float("nan"),
+            "rollouts_per_rank": [shard_range(R, r, world)[1] - shard_range(R, r, world)[0] for r in range(world)]}

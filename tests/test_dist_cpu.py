@@ -35,3 +35,53 @@ def test_gloo_two_rank_shard_and_gather(tmp_path):
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GATHER_OK" in out.stdout
+
+
+def test_gloo_two_rank_closed_loop_sharding(tmp_path):
+    """BASELINE config 5 host logic at world size 2: contiguous blocks of rollouts per rank, one launch per rank,
+    statistics gathered in rollout order on rank 0, device time = max over ranks.  The solver is a stand-in that
+    records what it was asked to run (the CUDA path itself is covered by the -m gpu tests)."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch.distributed as dist
+        from sde4mbrl_px4_b200 import sharding
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+
+        class FakeSolver:
+            def closed_loop(self, x0, t0, rng, ticks, want_hist=True):
+                assert not want_hist and ticks == 7
+                self.n = x0.shape[0]
+                st = np.stack([x0[:, 0], t0, rng[:, 0].astype(np.float32), np.full(self.n, ticks, np.float32)], axis=1)
+                return None, None, st.astype(np.float32)
+            def last_launch_ms(self):
+                return 100.0 * (r + 1)
+
+        R = 11
+        x0 = np.zeros((R, 13), np.float32); x0[:, 0] = np.arange(R)
+        t0 = np.arange(R, dtype=np.float32) * 0.25
+        rng = np.stack([1000 + np.arange(R), np.zeros(R)], axis=1).astype(np.uint64)
+        fs = FakeSolver()
+        out = sharding.closed_loop_sharded(fs, x0, t0, rng, 7)
+        lo, hi = sharding.shard_range(R, r, w)
+        assert fs.n == hi - lo
+        if r == 0:
+            st = out["stats"]
+            assert st.shape == (R, 4)
+            assert np.array_equal(st[:, 0], np.arange(R)) and np.array_equal(st[:, 1], t0)
+            assert np.array_equal(st[:, 2], 1000 + np.arange(R)) and np.all(st[:, 3] == 7)
+            assert abs(out["device_s"] - 0.1 * w) < 1e-6 and out["rollouts_per_rank"] == [6, 5]
+            assert abs(out["ticks_per_s"] - R * 7 / (0.1 * w)) < 1e-3
+            print("CLOSED_LOOP_OK")
+        else:
+            assert out is None
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "CLOSED_LOOP_OK" in out.stdout
