@@ -297,7 +297,7 @@ def main():
         x[0, 0:3] += [0.3, -0.2, 0.1]
         up, ip = s1.reset(1)
         rng1 = np.array([[10, 0]], np.uint64)
-        e2e_l, dev_l = [], []
+        e2e_l, dev_l, flop_l, it_l = [], [], [], []
         n_warm = 100
         for k in range(n_warm + args.latency_ticks):
             ct = np.array([0.05 * k], np.float32)
@@ -307,6 +307,8 @@ def main():
             if k >= n_warm:
                 e2e_l.append(dtm)
                 dev_l.append(float(ip[0, 7]) * 1e-3)
+                flop_l.append(algorithmic_flops(ip, H, P, F_STEP["iris"]))
+                it_l.append(float(ip[0, 2]))
             x = xe1[:, 1].copy()
             rng1[0, 1] += 1
         pc = lambda a, q: float(np.percentile(a, q))
@@ -314,6 +316,20 @@ def main():
                    "ticks": args.latency_ticks,
                    "e2e": {"p50": pc(e2e_l, 50), "p99": pc(e2e_l, 99), "max": float(np.max(e2e_l))},
                    "device": {"p50": pc(dev_l, 50), "p99": pc(dev_l, 99), "max": float(np.max(dev_l))}}
+        # the tick as a fraction of the FP32 roofline (north_star) and its dependent chain: a tick is one
+        # problem on the SMs of one cluster, so the whole-GPU fraction is tiny by construction; the chain length is
+        # the number that matters: every iteration is H forward + H adjoint step evaluations in sequence
+        pkl, ki1 = peaks(), s1.kernel_info()
+        ach = float(np.mean(flop_l)) / (pc(dev_l, 50) * 1e-3) / 1e12
+        sms = max(1, min(int(ki1["ctas"]), int(ki1["sm_count"])))
+        latency["roofline"] = {
+            "bound": "latency (dependent chain)", "algorithmic_flop_per_tick": float(np.mean(flop_l)),
+            "achieved_tflops": ach, "frac_of_gpu_fp32_peak": ach / pkl["fp32_tflops"], "sms_occupied": sms,
+            "frac_of_occupied_sms_fp32_peak": ach / (pkl["fp32_tflops"] * sms / int(ki1["sm_count"])),
+            "cycles_per_step_evaluation_on_the_critical_path":
+                pc(dev_l, 50) * 1e-3 * pkl["sm_max_mhz"] * 1e6 / (float(np.mean(it_l)) * 2 * H),
+            "kernel": ki1}
+        s1.close()
 
     # ---------------- tensor-core cost evaluation (supplementary: not the headline metric), rank 0 only ----------------
     tensor_path = None

@@ -5,8 +5,9 @@
 // body, the cost and the noise run per thread with the state in registers (every lane useful), and each network
 // layer is ONE dense contraction over the CTA's rows on the 5th-generation tensor cores:
 //     D[128 x N] (TMEM, fp32) = A[128 x K] (TMEM, written by the rows' own threads with tcgen05.st) * B[N x K]^T
-// with B = the layer's weights for BOTH networks staged once in shared memory (K-major, no swizzle; layer 2 and
-// the output layer are block diagonal over [drift | diffusion] columns).  The layer-1 bias rides on a constant-one
+// with B = the layer's weights for BOTH networks staged once in shared memory (K-major, no swizzle; layer 2 is
+// block diagonal over [drift | diffusion] columns and is contracted as two W x W blocks, the output layer as one
+// 16 x N12 operand with zero blocks).  The layer-1 bias rides on a constant-one
 // input (its K is padded to 16 anyway); the other biases are added in the epilogue so that a CTA needs only
 // 2 * N12 tensor-memory columns (128 for width 32: four CTAs per SM hide each other's MMA round trips).
 // kind::tf32: operands are read as TF32 (10-bit mantissa), accumulation is fp32, so this path is NOT SPEC-ARITH: it is compared with the oracle at a stated tolerance (tests/test_gpu_parity.py,
@@ -27,18 +28,22 @@ struct TCLayout {
     static constexpr int K2 = N12;                         // hidden units of both networks
     static constexpr int N3 = 16;                          // 6 + 6 outputs, padded
     // operand images: [rows / 8][K / 4 chunks][8 rows][16 bytes]
-    static constexpr int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128, LBO = 128;
+    static constexpr int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128, SBOW = (W / 4) * 128, LBO = 128;
+    // Layer 2 is block diagonal over [drift | diffusion]: it is stored and contracted as two W x W blocks (half the
+    // shared memory and half the tensor work of the N12 x N12 form; for width 64 this is what lets two CTAs of the
+    // adjoint variant share an SM).  NET2 = bytes of one block.
+    static constexpr int NET2 = (W / 8) * SBOW;
     static constexpr int B1 = 0;
     static constexpr int B2 = B1 + (N12 / 8) * SBO1;
-    static constexpr int B3 = B2 + (N12 / 8) * SBO2;
+    static constexpr int B3 = B2 + 2 * NET2;
     static constexpr int BIAS2 = B3 + (N3 / 8) * SBO2;     // float b2[N12], then float b3[16]
     static constexpr int BIAS3 = BIAS2 + N12 * 4;
     static constexpr int BYTES = BIAS3 + 16 * 4;           // forward image
-    // adjoint image (appended): transposed operands, no bias.  B3T [N12 rows x 16], B2T [N12 x N12], B1T [16 x N12]
+    // adjoint image (appended): transposed operands, no bias.  B3T [N12 rows x 16], B2T 2 x [W x W], B1T [16 x N12]
     static constexpr int SBO16 = (16 / 4) * 128;
     static constexpr int B3T = BYTES;
     static constexpr int B2T = B3T + (N12 / 8) * SBO16;
-    static constexpr int B1T = B2T + (N12 / 8) * SBO2;
+    static constexpr int B1T = B2T + 2 * NET2;
     static constexpr int BYTES_GRAD = B1T + (16 / 8) * SBO2;
     // activation / step tape of the adjoint in global memory, 16-byte granules laid out [step][granule][row]:
     // h1 (N12 halves), h2 (N12 halves), then 9 granules of floats: what the sweep reads of the step tape (r[0..2],
@@ -106,6 +111,7 @@ __device__ __forceinline__ void publish() {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // eight activations <-> one 16-byte tape granule of fp16 pairs
 __device__ __forceinline__ float4 pack8(const float* v) {
     const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]), c = __floats2half2_rn(v[4], v[5]),
@@ -178,7 +184,7 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
     const uint32_t tb = *tmem_base_slot;
     const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
     const uint32_t sb = tc::smem_u32(sB);
-    const uint32_t id12 = tc::idesc_tf32(128, N12), id3 = tc::idesc_tf32(128, L::N3);
+    const uint32_t id12 = tc::idesc_tf32(128, N12), id3 = tc::idesc_tf32(128, L::N3), idW = tc::idesc_tf32(128, W);
     uint32_t phase = 0;
 
     // row = problem * particles + particle: the particles of a problem are adjacent lanes of one warp (the
@@ -261,8 +267,11 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
         tc::publish();
         if (tid == 0) {
 #pragma unroll
-            for (int k8 = 0; k8 < L::K2 / 8; ++k8)
-                tc::mma_ts(tb + L::C_D12, tb + L::C_A + 8 * k8, tc::desc(sb + L::B2 + k8 * 2 * L::LBO, L::SBO2), id12, k8 > 0);
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int k8 = 0; k8 < W / 8; ++k8)
+                    tc::mma_ts(tb + L::C_D12 + n * W, tb + L::C_A + n * W + 8 * k8,
+                               tc::desc(sb + L::B2 + n * L::NET2 + k8 * 2 * L::LBO, L::SBOW), idW, k8 > 0);
             tc::commit(bar);
         }
         tc::wait(bar, phase); phase ^= 1;
@@ -366,6 +375,12 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
 #pragma unroll
         for (int i = 0; i < NU; ++i) gp[i] = 0.f;
         for (int t = P.H - 1; t >= 0; --t) {
+            // the sweep consumes its tape as it loads it (57 % of the stall samples were these loads): pull the previous
+            // step's granules into L2 while this step's contractions run (0.600 -> 0.576 ms; two or three steps ahead: no gain)
+            if (t > 0) {
+#pragma unroll
+                for (int g = 0; g < L::TG; ++g) tc::prefetch_l2(tp(t - 1, g));
+            }
             float xt[NX], xi[6];
             const float4 s0 = *tp(t, L::T_ST), s1 = *tp(t, L::T_ST + 1), s2 = *tp(t, L::T_ST + 2), s3 = *tp(t, L::T_ST + 3),
                          s4 = *tp(t, L::T_ST + 4);
@@ -421,8 +436,11 @@ __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char*
             tc::publish();
             if (tid == 0) {
 #pragma unroll
-                for (int k8 = 0; k8 < L::K2 / 8; ++k8)
-                    tc::mma_ts(tb + L::C_D12, tb + L::C_A + 8 * k8, tc::desc(sb + L::B2T + k8 * 2 * L::LBO, L::SBO2), id12, k8 > 0);
+                for (int n = 0; n < 2; ++n)
+#pragma unroll
+                    for (int k8 = 0; k8 < W / 8; ++k8)
+                        tc::mma_ts(tb + L::C_D12 + n * W, tb + L::C_A + n * W + 8 * k8,
+                                   tc::desc(sb + L::B2T + n * L::NET2 + k8 * 2 * L::LBO, L::SBOW), idW, k8 > 0);
                 tc::commit(bar);
             }
             tc::wait(bar, phase); phase ^= 1;

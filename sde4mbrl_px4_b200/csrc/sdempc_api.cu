@@ -533,8 +533,12 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
 }
 
 // Tensor-core batched rollout / value_and_grad (mpc_tc.cuh): 128 rows per CTA, thread = (problem, particle) = TMEM lane.
+// Resident CTAs per SM are bounded by tensor memory (512 columns): the register budget is set to allow exactly that many.
+#ifndef SDEMPC_TC_MIN_CTAS
+#define SDEMPC_TC_MIN_CTAS(NU, W) (512 / TCLayout<NU, W>::COLS)
+#endif
 template <int NU, int W, bool GRAD>
-__global__ void __launch_bounds__(128, 1) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(128, SDEMPC_TC_MIN_CTAS(NU, W)) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t tc_bar;
@@ -716,15 +720,16 @@ static void pack_weights(sdempc_handle* h) {
 }
 
 // Operand image of the tensor-core path (TCLayout in mpc_tc.cuh): K-major rows of [W1 | b1] (b1 multiplies a
-// constant-one input), block-diagonal W2 and W3 over the [drift | diffusion] hidden columns, then b2 and b3.
+// constant-one input), W2 as two W x W blocks (drift, diffusion), W3 block diagonal over the [drift | diffusion]
+// hidden columns, then b2 and b3.
 static void pack_weights_tc(sdempc_handle* h) {
     const int NU = h->mh.nu, W = h->mh.width, NIN = 6 + NU, N12 = 2 * W;
     const int K1 = ((NIN + 1 + 7) / 8) * 8, K2 = N12, N3 = 16;
-    const int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128;
-    const int B1 = 0, B2 = B1 + (N12 / 8) * SBO1, B3 = B2 + (N12 / 8) * SBO2, BIAS2 = B3 + (N3 / 8) * SBO2, BIAS3 = BIAS2 + N12 * 4,
+    const int SBO1 = (K1 / 4) * 128, SBO2 = (K2 / 4) * 128, SBOW = (W / 4) * 128, NET2 = (W / 8) * SBOW;
+    const int B1 = 0, B2 = B1 + (N12 / 8) * SBO1, B3 = B2 + 2 * NET2, BIAS2 = B3 + (N3 / 8) * SBO2, BIAS3 = BIAS2 + N12 * 4,
               BYTES = BIAS3 + 16 * 4;
     auto off = [](int sbo, int row, int k) { return ((row / 8) * sbo + (k / 4) * 128 + (row % 8) * 16 + (k % 4) * 4) / 4; };
-    const int SBO16 = (16 / 4) * 128, B3T = BYTES, B2T = B3T + (N12 / 8) * SBO16, B1T = B2T + (N12 / 8) * SBO2,
+    const int SBO16 = (16 / 4) * 128, B3T = BYTES, B2T = B3T + (N12 / 8) * SBO16, B1T = B2T + 2 * NET2,
               BYTES_GRAD = B1T + (16 / 8) * SBO2;
     h->wimg_tc.assign(BYTES_GRAD / 4, 0.f);
     float* I = h->wimg_tc.data();
@@ -740,11 +745,11 @@ static void pack_weights_tc(sdempc_handle* h) {
             const int row = n * W + j;
             for (int k = 0; k < NIN; ++k) I[B1 / 4 + off(SBO1, row, k)] = W1[j * NIN + k];
             I[B1 / 4 + off(SBO1, row, NIN)] = b1[j];   // multiplies the constant-one input
-            for (int k = 0; k < W; ++k) I[B2 / 4 + off(SBO2, row, n * W + k)] = W2[j * W + k];
+            for (int k = 0; k < W; ++k) I[(B2 + n * NET2) / 4 + off(SBOW, j, k)] = W2[j * W + k];   // block n of layer 2
             I[BIAS2 / 4 + row] = b2[j];
             // adjoint operands: row = the hidden column that receives the adjoint
             for (int o = 0; o < 6; ++o) I[B3T / 4 + off(SBO16, row, n * 6 + o)] = W3[o * W + j];          // (W3^T)[j][o]
-            for (int k = 0; k < W; ++k) I[B2T / 4 + off(SBO2, row, n * W + k)] = W2[k * W + j];           // (W2^T)[j][k]
+            for (int k = 0; k < W; ++k) I[(B2T + n * NET2) / 4 + off(SBOW, j, k)] = W2[k * W + j];         // (W2^T)[j][k], block n
             for (int i = 0; i < NIN; ++i) I[B1T / 4 + off(SBO2, i, row)] = W1[j * NIN + i];               // (W1^T)[i][j]
         }
         for (int o = 0; o < 6; ++o) {
