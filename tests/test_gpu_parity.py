@@ -464,6 +464,33 @@ def test_closed_loop_monte_carlo(solver, O):
     _eq(a[0], b[0], "P=8 plant trajectory"); _eq(a[2], b[2], "P=8 stats")
 
 
+def test_sharded_closed_loop_tool_matches_the_oracle(O):
+    """tools/closed_loop_mc.py (config 5 driver: sharding.closed_loop_sharded around sdempc_closed_loop) as a
+    single-rank job: its gathered statistics equal the oracle's closed loop on the same rollouts."""
+    from sde4mbrl_px4_b200 import config, model_io
+
+    R, ticks, iters = 12, 6, 10
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "closed_loop_mc.py"), "--rollouts", str(R), "--ticks", str(ticks),
+                          "--iters", str(iters)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 1 and line["rollouts_per_gpu"] == [R] and line["ticks_per_s"] > 0
+    # the same rollouts through the oracle (inputs exactly as the tool builds them)
+    cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
+    cfg = config.build_config(cfgd, max_iter=iters, rtol=0.0, atol=0.0)
+    o = O.Oracle(cfg, model_io.synthetic_model("iris").to_blob(), "f32")
+    tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.0, duration=60.0))
+    o.set_trajectory(tab)
+    x0 = synthetic.initial_states(tab[0, 1:4], R, seed=7)
+    t0 = np.random.default_rng(3).uniform(0, 8, R).astype(np.float32)
+    x0[:, 0:3] += trajectory.interp_table(tab, t0)[:, 0:3] - tab[0, 1:4]
+    rng = np.array([[9000 + r, 0] for r in range(R)], np.uint64)
+    st = o.closed_loop(x0, t0, rng, ticks)[2]
+    assert abs(line["rms_tracking_error_m"]["median"] - float(np.median(st[:, 0]))) <= 1e-6
+    assert abs(line["rms_tracking_error_m"]["max"] - float(st[:, 0].max())) <= 1e-6
+    assert abs(line["mean_opt_cost"] - float(st[:, 2].mean())) <= 1e-4 * abs(float(st[:, 2].mean()))
+
+
 def test_non_finite_state_is_reported_not_fatal(solver):
     cfg, blob, _ = make_setup("iris", "pos", max_iter=5)
     s = solver.MPCSolver(cfg, blob)
