@@ -350,14 +350,14 @@ def main():
             for name, c in cfgs.items():
                 sr = solver.MPCSolver(c, blob_v, device=local)
                 ms = []
-                for _ in range(4):
+                for _ in range(8):
                     Jr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=False)[0]
                     ms.append(sr.last_launch_ms())
                 msg = []
-                for _ in range(3):
+                for _ in range(6):
                     gr = sr.rollout(prt["x"], ut, upt, xref_win=prt["xref_win"], rng=prt["rng"], want_grad=True)[1]
                     msg.append(sr.last_launch_ms())
-                res[name] = (float(np.median(ms[1:])), Jr, float(np.median(msg[1:])), gr)
+                res[name] = (float(np.median(ms[3:])), Jr, float(np.median(msg[2:])), gr)   # warm-up launches dropped
                 sr.close()
             f, t = res["fp32"], res["tcgen05_tf32"]
             rows = Bt * particles
