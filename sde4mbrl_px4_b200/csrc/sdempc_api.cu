@@ -606,8 +606,15 @@ static KernelChoice make_choice() {
     {   // one tensor-core kernel per (nu, width): the particle count is a run-time row mapping
         k.rollout_tc = mpc_tc_rollout_kernel<NU, W, false>;
         k.rollout_tc_grad = mpc_tc_rollout_kernel<NU, W, true>;
-        k.tc_bytes = TCLayout<NU, W>::BYTES;
-        k.tc_bytes_grad = TCLayout<NU, W>::BYTES_GRAD;
+        // Residency must be bounded by tensor memory (512 / COLS CTAs per SM), never exceed it: a CTA that the block
+        // scheduler places beyond that spins in tcgen05.alloc while holding its slot (width 64, forward variant:
+        // registers and shared memory allowed three CTAs, tensor memory two -- launches were bimodal, 0.30 / 0.41 ms).
+        // Where registers do not already impose the bound, the dynamic shared-memory request is padded so that one
+        // more CTA cannot fit (228 KB per SM, 1 KB reserved per CTA).
+        constexpr int tmem_ctas = 512 / TCLayout<NU, W>::COLS;
+        constexpr int pad = tmem_ctas < 4 ? (228 * 1024) / (tmem_ctas + 1) + 1024 : 0;
+        k.tc_bytes = std::max(TCLayout<NU, W>::BYTES, pad);
+        k.tc_bytes_grad = std::max(TCLayout<NU, W>::BYTES_GRAD, pad);
         k.tc_tape_granules = TCLayout<NU, W>::TG;
     }
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
