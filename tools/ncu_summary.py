@@ -35,6 +35,7 @@ rows = list(csv.reader(io.StringIO(src)))
 h = rows[1]
 ix = {c: i for i, c in enumerate(h)}
 byop, stall, tot = collections.Counter(), collections.Counter(), 0
+stall_op = collections.Counter()   # stall samples attributed to the opcode the warp was waiting to issue
 scols = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
 for r in rows[2:]:
     if len(r) != len(h):
@@ -46,6 +47,7 @@ for r in rows[2:]:
     tot += ex
     for c in scols:
         stall[c] += int(r[ix[c]])
+        stall_op[op] += int(r[ix[c]])
 lines.append(f"\n# executed warp-instructions by opcode (total {tot})")
 for op, c in byop.most_common(16):
     lines.append(f"{op:10s} {100.0 * c / tot:6.2f} %")
@@ -53,5 +55,8 @@ ts = sum(stall.values())
 lines.append("\n# warp stall samples (all samples)")
 for k, v in stall.most_common(9):
     lines.append(f"{k:24s} {100.0 * v / ts:6.2f} %")
+lines.append("\n# warp stall samples by the opcode waiting to issue (where the latency is exposed)")
+for op, c in stall_op.most_common(10):
+    lines.append(f"{op:10s} {100.0 * c / max(ts, 1):6.2f} %")
 open(out, "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))
