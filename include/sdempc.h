@@ -38,7 +38,7 @@ extern "C" {
 
 #define SDEMPC_NX 13          /* state dimension (sde_control.py:246)            */
 #define SDEMPC_MAX_NU 8       /* iris 4, hexa 6 (launch/hexa_sitl_traj_mpc.yaml:7) */
-#define SDEMPC_MAX_H 32       /* horizon; every shipped config uses 20            */
+#define SDEMPC_MAX_H 32       /* array bound; horizon <= SDEMPC_MAX_H - 1 = 31 (rows 0..H of the window fit one warp); every shipped config uses 20 */
 #define SDEMPC_NNOISE 6       /* noisy state rows: v(3), w(3)                     */
 #define SDEMPC_TRACE_W 8      /* floats per iteration in the decision trace       */
 
@@ -73,7 +73,7 @@ extern "C" {
  */
 typedef struct sdempc_config {
     int32_t nu;                      /* len(input_constr.input_id), yaml:10                */
-    int32_t horizon;                 /* yaml:44                                            */
+    int32_t horizon;                 /* yaml:44; 1 .. SDEMPC_MAX_H - 1                     */
     int32_t num_particles;           /* yaml:52                                            */
     int32_t max_iter;                /* apg_mpc.max_iter, yaml:59                          */
     int32_t max_no_improvement_iter; /* yaml:60                                            */

@@ -145,7 +145,8 @@ void oracle_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { or
 #endif
 
 static void FN(box_muller)(uint32_t a, uint32_t b, REAL* n0, REAL* n1) {
-    /* uniforms in (0,1) on a 2^-24 grid: exactly representable in float32 */
+    /* uniforms in (0,1] from the top 24 bits, float32 arithmetic: for a >> 8 >= 2^23 the half-cell offset
+     * rounds to even (u = 1 is reachable, u = 0 is not), tests/test_independent_apg.py restates this */
     float u1 = ((float)(a >> 8) + 0.5f) * 5.9604644775390625e-08f;
     float u2 = ((float)(b >> 8) + 0.5f) * 5.9604644775390625e-08f;
     REAL rad = R_SQRT((REAL)-2 * M_LOG((REAL)u1));

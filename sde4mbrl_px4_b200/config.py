@@ -55,8 +55,8 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
     if ids != list(range(nu)) or nu > _abi.MAX_NU:
         raise ConfigError(f"input_constr.input_id must be 0..nu-1 with nu <= {_abi.MAX_NU}, got {ids}")
     H = int(cfg["horizon"])
-    if not 1 <= H <= _abi.MAX_H:
-        raise ConfigError(f"horizon must be in 1..{_abi.MAX_H}")
+    if not 1 <= H <= _abi.MAX_H - 1:   # the kernels handle rows 0..H of the window with one lane per row
+        raise ConfigError(f"horizon must be in 1..{_abi.MAX_H - 1}")
     c.nu, c.horizon = nu, H
     c.num_particles = int(overrides.get("num_particles", cfg.get("num_particles", 1)))
     apg = cfg["apg_mpc"]
@@ -130,6 +130,12 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
     c.atol = float(overrides.get("atol", apg.get("atol", 0.0)))
     c.rtol = float(overrides.get("rtol", apg.get("rtol", 0.0)))
     c.beta_init = float(apg.get("beta_init", 0.25))
+    if c.beta_init != 0.25:
+        # the momentum rule is beta_k = k / (k + 3) (launch/iris_sitl_traj_mpc.yaml:63-66), whose first value is 1/4
+        msg = f"apg_mpc.beta_init = {c.beta_init} is not applied: the solver uses beta_k = k / (k + 3) (beta_1 = 0.25)"
+        if strict:
+            raise ConfigError(msg)
+        warnings.warn(msg)
 
     unsupported = [k for k in _UNSUPPORTED_COST_KEYS if k in cp] + [k for k in _UNSUPPORTED_TOP_KEYS if k in cfg]
     if apg.get("moment_scale", None) is not None:

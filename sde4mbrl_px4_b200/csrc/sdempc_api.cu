@@ -841,7 +841,10 @@ static void build_kparams(sdempc_handle* h) {
 }
 
 static int ensure_device(sdempc_handle* h) {
-    if (h->dev_ready) return 0;
+    if (h->dev_ready) {   // several handles on different GPUs may share a thread: always select this handle's device
+        CUDA_TRY(cudaSetDevice(h->device));
+        return 0;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -931,7 +934,7 @@ static bool use_group(const sdempc_handle* h, int B) {
 static int ensure_mtape_group(sdempc_handle* h, int grid) {
     const size_t tapes = (size_t)grid * GROUP_GW * h->kc.gp;
     if (tapes <= h->mtape_group_n) return 0;
-    if (h->d_mtape_group) cudaFree(h->d_mtape_group); cudaFree(h->d_wimg_tc); cudaFree(h->d_tape_tc);
+    if (h->d_mtape_group) cudaFree(h->d_mtape_group);
     h->d_mtape_group = nullptr;
     CUDA_TRY(cudaMalloc(&h->d_mtape_group, tapes * (size_t)h->cfg.horizon * 2 * h->mh.width * sizeof(float2)));
     h->mtape_group_n = tapes;
@@ -1114,7 +1117,8 @@ int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbyte
     if (mh.magic != SDEMPC_MODEL_MAGIC || mh.version != SDEMPC_MODEL_VERSION) return fail(SDEMPC_EINVAL, "bad model magic/version");
     if (mh.n_hidden != 2 || mh.n_out != 6 || mh.n_in != 6 + mh.nu) return fail(SDEMPC_EINVAL, "unsupported network shape");
     if (cfg->nu != mh.nu) return fail(SDEMPC_EINVAL, "config nu=%d does not match model nu=%d", cfg->nu, mh.nu);
-    if (cfg->horizon < 1 || cfg->horizon > SDEMPC_MAX_H) return fail(SDEMPC_EINVAL, "horizon out of range 1..%d", SDEMPC_MAX_H);
+    // the kernels build the reference window and write x_evol with one lane per row (rows 0..H): H + 1 <= 32
+    if (cfg->horizon < 1 || cfg->horizon > SDEMPC_MAX_H - 1) return fail(SDEMPC_EINVAL, "horizon out of range 1..%d", SDEMPC_MAX_H - 1);
     if (cfg->max_iter < 1 || cfg->maxls < 0) return fail(SDEMPC_EINVAL, "max_iter must be >= 1 and maxls >= 0");
     const int W = mh.width, NIN = mh.n_in;
     const size_t per_net = (size_t)W * NIN + W + (size_t)W * W + W + 6 * (size_t)W + 6;
@@ -1142,7 +1146,7 @@ void sdempc_destroy(sdempc_t* h) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
         cudaFree(h->d_wimg); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_mtape_group); cudaFree(h->d_in); cudaFree(h->d_out);
-        cudaFree(h->d_trace); cudaFree(h->d_flush);
+        cudaFree(h->d_trace); cudaFree(h->d_flush); cudaFree(h->d_wimg_tc); cudaFree(h->d_tape_tc);
         if (h->h_in) cudaFreeHost(h->h_in);
         if (h->h_out) cudaFreeHost(h->h_out);
         if (h->ev0) cudaEventDestroy(h->ev0);

@@ -100,15 +100,26 @@ class MPCController:
         i = info[0]
         return OptState(_wrap(u[0]), *[float(v) for v in i[:7]], 0.0)
 
-    def m_mpc(self, x, rng, opt_state: OptState, curr_t=0.0, xdes=None):
+    def m_mpc(self, x, rng, opt_state: OptState, curr_t=0.0, xdes=None, shift: int = 1):
         """One MPC solve.  Trajectory controllers track ``state_from_traj(curr_t + ...)`` and ignore
-        ``xdes`` ("xdes does not matter here", sde_control.py:408); set-point controllers track ``xdes``."""
+        ``xdes`` ("xdes does not matter here", sde_control.py:408); set-point controllers track ``xdes``.
+
+        Warm start: the solve shifts ``opt_state.yk`` left by one step (last row repeated) and uses its
+        first row as the control being applied (slew reference), i.e. it assumes ONE solve per ``dt[0]``
+        — the rate the node runs at (``_dt_usec_*`` = ``_time_steps[0]``, sde_control.py:167-177).  A
+        caller that solves every n-th step passes ``shift=n``: the plan is advanced n - 1 further rows
+        here, so the first row handed to the library is the control applied during the last elapsed step."""
         x = np.asarray(x, np.float32).reshape(1, 13)
         rng = np.asarray(rng, np.uint64).reshape(1, 2)
+        plan = np.asarray(opt_state.yk, np.float32)
+        if shift < 1:
+            raise ValueError("shift must be >= 1 (SDEMPC_F_NO_SHIFT / no_shift=True disables the shift for a handle)")
+        if shift > 1:
+            k = min(shift - 1, self.H - 1)
+            plan = np.concatenate([plan[k:], np.repeat(plan[-1:], k, axis=0)], axis=0)
         kw = dict(curr_t=np.asarray([curr_t], np.float32)) if self.has_trajectory else dict(
             xdes=np.asarray(x if xdes is None else xdes, np.float32).reshape(1, 13))
-        u, xe, info, _ = self.solver.solve(x, np.asarray(opt_state.yk, np.float32)[None], opt_state.info_array()[None],
-                                           rng=rng, **kw)
+        u, xe, info, _ = self.solver.solve(x, plan[None], opt_state.info_array()[None], rng=rng, **kw)
         i = info[0]
         new_state = OptState(_wrap(u[0]), *[float(v) for v in i[:8]])
         new_rng = rng[0].copy()

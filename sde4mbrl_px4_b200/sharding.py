@@ -67,17 +67,65 @@ class _DevBuf:
 _gather_cache: dict = {}
 
 
-def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
-    """One batched solve of this rank's shard followed by the final result gather **device to device**:
-    inputs go host -> HBM (pinned staging), the solve kernel runs, every rank's OUT block (x_evol | plan |
-    telemetry) is gathered over NCCL / NVLink straight from the library's device buffer (one all_gather per
-    sub-array, so the gathered arrays are contiguous), and rank 0 copies them once into pinned host memory.
-    Returns the dict of [B_total, ...] arrays on rank 0 (views of reused pinned buffers), else None.
-    This is the only collective of the path."""
+def gather_to_rank0(parts: dict, bufs: dict | None = None) -> dict | None:
+    """True gather (rank 0 is the only receiver) of equally shaped per-rank tensors: ``parts[name]`` is this rank's
+    flat float32 tensor (CPU for gloo, CUDA for NCCL).  Returns ``{name: [world, n] tensor}`` on rank 0 (in pinned
+    host memory when the inputs are CUDA tensors), None elsewhere.  For CUDA inputs the device-to-host copy of
+    array k runs on a side stream while array k + 1 is still being gathered.  ``bufs`` caches the receive / pinned
+    buffers between calls."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(), dist.get_rank()
+    bufs = {} if bufs is None else bufs
+    names = sorted(parts.keys())
+    cuda = parts[names[0]].is_cuda
+    if cuda and "_copy_stream" not in bufs:
+        bufs["_copy_stream"] = torch.cuda.Stream()
+    out = {}
+    events = []
+    for k in names:
+        t = parts[k]
+        n = t.numel()
+        if rank == 0:
+            if k not in bufs or bufs[k][0].shape != (world, n):
+                recv = torch.empty((world, n), dtype=torch.float32, device=t.device)
+                host = torch.empty((world, n), dtype=torch.float32, pin_memory=True) if cuda else recv
+                bufs[k] = (recv, host)
+            recv, host = bufs[k]
+            dist.gather(t, gather_list=list(recv.unbind(0)), dst=0)
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record()                                  # the current stream has waited for the gather
+                with torch.cuda.stream(bufs["_copy_stream"]):
+                    bufs["_copy_stream"].wait_event(ev)
+                    host.copy_(recv, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record()
+                events.append(done)
+            out[k] = host
+        else:
+            dist.gather(t, gather_list=None, dst=0)
+    if cuda:
+        if rank == 0:
+            for ev in events:
+                ev.synchronize()
+        else:
+            torch.cuda.current_stream().synchronize()        # the send has left this rank's OUT block
+    return out if rank == 0 else None
+
+
+def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
+    """One batched solve of this rank's shard followed by the final result gather **device to device**:
+    inputs go host -> HBM (pinned staging), the solve kernel runs, every rank's OUT block (x_evol | plan |
+    telemetry) is sent over NCCL / NVLink straight from the library's device buffer to rank 0 only (one gather
+    per sub-array, so the gathered arrays are contiguous), and rank 0 copies each array into pinned host memory
+    while the next one is still in flight.  Returns the dict of [B_total, ...] arrays on rank 0 (views of reused
+    pinned buffers), else None.  This is the only collective of the path."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
     sizes = [shard_range(B_total, r, world)[1] - shard_range(B_total, r, world)[0] for r in range(world)]
     if len(set(sizes)) != 1:
         raise ValueError("solve_sharded needs equal shards (B_total divisible by the world size)")
@@ -86,30 +134,16 @@ def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
     solver.launch_timed(1, flush_l2=False)          # launch + event wait on the handle's stream
     ptr, nbytes, layout = solver.device_out()
     local = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
+    parts = {k: local[off // 4: off // 4 + int(np.prod(shape))] for k, (off, shape) in layout.items()}
     key = (world, tuple((k, off, shape) for k, (off, shape) in sorted(layout.items())))
-    if key not in _gather_cache:
-        bufs = {}
-        for k, (off, shape) in layout.items():
-            n = int(np.prod(shape))
-            dev = torch.empty((world, n), dtype=torch.float32, device="cuda")
-            host = torch.empty((world, n), dtype=torch.float32, pin_memory=True) if rank == 0 else None
-            bufs[k] = (dev, host)
+    if _gather_cache.get("key") != key:
         _gather_cache.clear()
-        _gather_cache[key] = bufs
-    bufs = _gather_cache[key]
-    for k, (off, shape) in layout.items():
-        n = int(np.prod(shape))
-        dist.all_gather_into_tensor(bufs[k][0], local[off // 4: off // 4 + n])   # ~1.5 KB per problem in total
-    if rank != 0:
-        torch.cuda.current_stream().synchronize()
+        _gather_cache["key"] = key
+        _gather_cache["bufs"] = {}
+    got = gather_to_rank0(parts, _gather_cache["bufs"])   # ~1.5 KB per problem in total
+    if got is None:
         return None
-    res = {}
-    for k, (off, shape) in layout.items():
-        bufs[k][1].copy_(bufs[k][0], non_blocking=True)                            # one D2H per array, pinned
-    torch.cuda.current_stream().synchronize()
-    for k, (off, shape) in layout.items():
-        res[k] = bufs[k][1].numpy().reshape((world * shape[0],) + tuple(shape[1:]))
-    return res
+    return {k: got[k].numpy().reshape((world * shape[0],) + tuple(shape[1:])) for k, (off, shape) in layout.items()}
 
 
 def closed_loop_sharded(solver, x0, t0, rng, ticks: int, device=None) -> dict | None:

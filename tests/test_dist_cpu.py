@@ -37,6 +37,39 @@ def test_gloo_two_rank_shard_and_gather(tmp_path):
     assert "GATHER_OK" in out.stdout
 
 
+def test_gloo_two_rank_gather_to_rank0(tmp_path):
+    """The collective inside sharding.solve_sharded (a true gather: rank 0 is the only receiver), on gloo."""
+    script = tmp_path / "g.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch, torch.distributed as dist
+        from sde4mbrl_px4_b200 import sharding
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        bufs = {{}}
+        for rep in range(2):                       # second call reuses the cached receive buffers
+            parts = {{"u": torch.arange(12, dtype=torch.float32) + 100 * r + rep, "info": torch.full((8,), float(r + rep))}}
+            out = sharding.gather_to_rank0(parts, bufs)
+            if r == 0:
+                assert out["u"].shape == (w, 12) and out["info"].shape == (w, 8)
+                for q in range(w):
+                    assert torch.equal(out["u"][q], torch.arange(12, dtype=torch.float32) + 100 * q + rep)
+                    assert torch.equal(out["info"][q], torch.full((8,), float(q + rep)))
+            else:
+                assert out is None
+        if r == 0:
+            print("GATHER0_OK")
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GATHER0_OK" in out.stdout
+
+
 def test_gloo_two_rank_closed_loop_sharding(tmp_path):
     """BASELINE config 5 host logic at world size 2: contiguous blocks of rollouts per rank, one launch per rank,
     statistics gathered in rollout order on rank 0, device time = max over ranks.  The solver is a stand-in that

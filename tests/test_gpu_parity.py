@@ -334,7 +334,7 @@ def test_tensor_core_rollout_with_particles(solver, O, vehicle, particles):
 
 @pytest.mark.parametrize("seed", list(range(24)))
 def test_randomised_configurations(solver, O, seed):
-    """Seeded fuzz over the configuration space (horizon 4..32, step grid, discount, cost weights, bounds, line-search
+    """Seeded fuzz over the configuration space (horizon 4..31, step grid, discount, cost weights, bounds, line-search
     constants, maxls 0..6, particles, vehicle, frame, batch size -> kernel choice): solve + value_and_grad stay
     bit-identical to the oracle."""
     import os
@@ -346,7 +346,7 @@ def test_randomised_configurations(solver, O, seed):
     vehicle = ["iris", "hexa"][seed % 2]
     P = int(rng.choice([1, 1, 2, 4, 8])) if vehicle == "iris" else int(rng.choice([1, 8]))
     cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{vehicle}_traj.yaml"))
-    H = int(rng.integers(4, 33))
+    H = int(rng.integers(4, 32))
     nu = 4 if vehicle == "iris" else 6
     cfgd.update(horizon=H, num_short_dt=int(rng.integers(0, H + 1)), short_step_dt=float(rng.uniform(0.02, 0.06)),
                 long_step_dt=float(rng.uniform(0.05, 0.12)), discount=float(rng.uniform(0.9, 1.0)), num_particles=P)
@@ -489,6 +489,114 @@ def test_sharded_closed_loop_tool_matches_the_oracle(O):
     assert abs(line["rms_tracking_error_m"]["median"] - float(np.median(st[:, 0]))) <= 1e-6
     assert abs(line["rms_tracking_error_m"]["max"] - float(st[:, 0].max())) <= 1e-6
     assert abs(line["mean_opt_cost"] - float(st[:, 2].mean())) <= 1e-4 * abs(float(st[:, 2].mean()))
+
+
+def test_positional_sdempc_solve_as_integration_md_binds_it(solver, O):
+    """The positional `sdempc_solve` of include/sdempc.h, called through raw ctypes exactly as INTEGRATION.md
+    section 2 shows (create -> set_trajectory -> reset -> per-tick solve with in/out plan and info), equals
+    `sdempc_solve_ex` through the Python front end and the oracle, over three warm-started ticks."""
+    import ctypes as C
+
+    from sde4mbrl_px4_b200 import _abi
+
+    cfg, blob, _ = make_setup("iris", "traj", max_iter=25, rtol=0.0, atol=0.0)
+    lib = C.CDLL(os.path.join(ROOT, "sde4mbrl_px4_b200", "libsdempc.so"))
+    lib.sdempc_last_error.restype = C.c_char_p
+    table = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.0, duration=20.0))
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    h = C.c_void_p()
+    assert lib.sdempc_create(C.byref(cfg), blob, C.c_size_t(len(blob)), 0, C.byref(h)) == 0
+    assert lib.sdempc_set_trajectory(h, fp(table), len(table)) == 0
+    H, nu = cfg.horizon, cfg.nu
+    u_plan = np.zeros((1, H, nu), np.float32)
+    info = (_abi.Info * 1)()
+    assert lib.sdempc_reset(h, 1, None, None, fp(u_plan), info) == 0
+    s2 = solver.MPCSolver(cfg, blob); s2.set_trajectory(table)
+    o = O.Oracle(cfg, blob, "f32"); o.set_trajectory(table)
+    up2, ip2 = s2.reset(1)
+    upo, ipo = o.reset(1)
+    x = table[0:1, 1:].copy(); x[0, 0:3] += [0.2, -0.1, 0.05]
+    rng = np.array([10, 0], np.uint64)
+    for k in range(3):
+        ct = np.float32([0.05 * k])
+        x_evol = np.zeros((1, H + 1, 13), np.float32)
+        rc = lib.sdempc_solve(h, 1, fp(x), fp(ct), None, rng.ctypes.data_as(C.POINTER(C.c_uint64)), fp(u_plan), fp(x_evol), info, None)
+        assert rc == 0, lib.sdempc_last_error().decode()
+        up2, xe2, ip2, _ = s2.solve(x, up2, ip2, curr_t=ct, rng=rng[None])
+        upo, xeo, ipo, _ = o.solve(x, upo, ipo, curr_t=ct, rng=rng[None])
+        inf = np.frombuffer(info, dtype=np.float32).reshape(1, 8)
+        _eq(u_plan, up2, f"tick {k}: positional vs ex plan"); _eq(x_evol, xe2, f"tick {k}: positional vs ex x_evol")
+        _eq(inf[:, :7], ip2[:, :7], f"tick {k}: positional vs ex telemetry")
+        _eq(u_plan, upo, f"tick {k}: positional vs oracle plan"); _eq(x_evol, xeo, f"tick {k}: positional vs oracle x_evol")
+        _eq(inf[:, :7], ipo[:, :7], f"tick {k}: telemetry vs oracle")
+        assert inf[0, 7] > 0, "solve_time_us is filled"
+        x = x_evol[:, 1].copy()
+        rng[1] += 1
+    lib.sdempc_destroy.argtypes = [C.c_void_p]
+    lib.sdempc_destroy(h)
+
+
+def test_group_solve_then_tensor_rollout_on_one_handle(solver, O):
+    """Buffer lifetime: a throughput-kernel solve followed by a tensor-core rollout on the SAME handle,
+    then a larger solve (activation-tape growth) and the rollout again; every result stays correct."""
+    cfg, blob, _ = make_setup("iris", "traj", max_iter=6, rtol=0.0, atol=0.0, group=True, tensor=True)
+    s, o = solver.MPCSolver(cfg, blob), O.Oracle(cfg, blob, "f32")
+    for B in (40, 700, 40):
+        pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=B)
+        u0, i0 = s.reset(B)
+        a = s.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+        b = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+        if not (cfg.flags & 64):   # SDEMPC_F_TENSOR also selects the tensor-core solve once it exists; then not bit-exact
+            _eq(a[0], b[0], f"B={B} plan")
+        Jt, gt, _ = s.rollout(pr["x"], u0, u0[:, 0], xref_win=pr["xref_win"], rng=pr["rng"])
+        Jo, go, _ = o.rollout(pr["x"], u0, u0[:, 0], xref_win=pr["xref_win"], rng=pr["rng"])
+        assert np.max(np.abs(Jt - Jo) / np.abs(Jo)) <= 1e-4, f"B={B} tensor-core cost after a group solve"
+        assert np.max(np.abs(gt - go)) <= 1e-3 * np.max(np.abs(go)), f"B={B} tensor-core gradient after a group solve"
+    s.close()
+
+
+def test_solve_sharded_two_gpus_matches_the_oracle(O):
+    """sharding.solve_sharded (H2D, solve, device-to-device gather of every rank's OUT block to rank 0, D2H) on two
+    ranks == the oracle on the concatenated batch.  Needs 2 GPUs (`gpurun --gpus 2`); skipped otherwise."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r}); sys.path.insert(0, os.path.join({ROOT!r}, "tests"))
+        import numpy as np, torch, torch.distributed as dist
+        from conftest import make_setup
+        from sde4mbrl_px4_b200 import sharding, solver, synthetic
+        r, w = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        torch.cuda.set_device(r)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", r))
+        cfg, blob, _ = make_setup("iris", "traj", max_iter=12, rtol=0.0, atol=0.0)
+        B = 2 * 300
+        pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=5)
+        loc = sharding.shard_problem(pr, r, w)
+        s = solver.MPCSolver(cfg, blob, device=r)
+        u0, i0 = s.reset(B // w)
+        for rep in range(2):                      # the second call reuses the cached gather buffers
+            g = sharding.solve_sharded(s, loc, u0, i0, B)
+        if r == 0:
+            from oracle import oracle as O
+            o = O.Oracle(cfg, blob, "f32")
+            uo, xo, io, _ = o.solve(pr["x"], np.tile(u0[:1], (B, 1, 1)), np.tile(i0[:1], (B, 1)), xref_win=pr["xref_win"], rng=pr["rng"])
+            assert np.array_equal(g["u"], uo) and np.array_equal(g["x_evol"], xo) and np.array_equal(g["info"][:, :7], io[:, :7])
+            print("SHARDED_OK")
+        else:
+            assert g is None
+        dist.barrier(); dist.destroy_process_group()
+    """)
+    path = os.path.join(ROOT, "gpurun_out", "_sharded_test.py")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    open(path, "w").write(script)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29547", path], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert "SHARDED_OK" in out.stdout
 
 
 def test_non_finite_state_is_reported_not_fatal(solver):

@@ -204,3 +204,46 @@ def test_jit_shim_and_optstate_contract():
     k = design.PRNGKey(10)
     ks = design.split(k, 3)
     assert ks.shape == (3, 2) and len({int(v) for v in ks[:, 0]}) == 3 and np.all(ks[:, 1] == 0)
+
+
+def test_integration_md_import_lines_work_verbatim():
+    """The two import lines INTEGRATION.md section 1 tells a maintainer to write (the reference's own lines at
+    sde_control.py:12-13 with only the package name changed) are executed exactly as printed there."""
+    import re
+
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    lines = re.findall(r"^\+(from sde4mbrl_px4_b200\.rotor_uav\.\S+ import \S+)\s*$", txt, flags=re.M)
+    assert len(lines) == 2, lines
+    ns = {}
+    for ln in lines:
+        exec(ln, ns)
+    assert ns["load_mpc_from_cfgfile"] is design.load_mpc_from_cfgfile
+    from sde4mbrl_px4_b200 import utils
+    assert ns["enu2ned"] is utils.enu2ned
+    # same module layout as the reference's `sde4mbrlExamples.rotor_uav.{sde_mpc_design,utils}`: real submodules
+    import importlib
+    assert importlib.import_module("sde4mbrl_px4_b200.rotor_uav.sde_mpc_design").__name__.endswith("rotor_uav.sde_mpc_design")
+    assert importlib.import_module("sde4mbrl_px4_b200.rotor_uav.utils").enu2ned is utils.enu2ned
+    import sde4mbrl_px4_b200 as pkg
+    assert pkg.load_mpc_from_cfgfile is design.load_mpc_from_cfgfile and pkg.enu2ned is utils.enu2ned
+
+
+def test_horizon_bound_and_beta_init_are_checked():
+    """horizon <= 31 (rows 0..H of the reference window are built by one lane each) is enforced by the YAML layer AND
+    by sdempc_create; a beta_init other than 1/4 is reported (the momentum rule k/(k+3) fixes it, yaml:63-69)."""
+    from sde4mbrl_px4_b200 import solver
+    d = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
+    d32 = dict(d, horizon=32, num_short_dt=32)
+    with pytest.raises(config.ConfigError, match="horizon"):
+        config.build_config(d32)
+    c = config.build_config(dict(d, horizon=31, num_short_dt=31))
+    blob = model_io.synthetic_model("iris").to_blob()
+    solver.MPCSolver(c, blob).close()
+    c.horizon = 32
+    with pytest.raises(RuntimeError, match="horizon out of range"):
+        solver.MPCSolver(c, blob)
+    db = dict(d, apg_mpc=dict(d["apg_mpc"], beta_init=0.5))
+    with pytest.warns(UserWarning, match="beta_init"):
+        config.build_config(db)
+    with pytest.raises(config.ConfigError, match="beta_init"):
+        config.build_config(db, strict=True)
