@@ -157,6 +157,32 @@ class Oracle:
             raise RuntimeError(f"oracle solve failed: {rc}")
         return u, xe, info, trace
 
+    def solve_forced(self, x, u_plan, info, forced_trace, forced_iters, curr_t=None, xdes=None, xref_win=None, rng=None, xi=None):
+        """Teacher-forced replay: the trial counts, accept / reject decisions and iteration counts come from
+        ``forced_trace[B, max_iter, 8]`` / ``forced_iters[B]`` (another solver's decision trace); returns
+        (u_plan', x_evol, info', trace, own) with ``own[B, max_iter, 4]`` = (this oracle's own trial count, own
+        accept, Armijo margin of the last forced trial, accept margin J_x - J_trial) per iteration."""
+        x = self._a(x, (-1, 13))
+        B = x.shape[0]
+        u = self._a(u_plan, (B, self.H, self.nu)).copy()
+        info = self._a(info, (B, 8)).copy()
+        curr_t, xdes = self._a(curr_t, (B,)), self._a(xdes, (B, 13))
+        xref_win = self._a(xref_win, (B, self.H + 1, 13))
+        xi = self._a(xi, (B, self.P, self.H, 6))
+        rng = None if rng is None else np.ascontiguousarray(rng, np.uint64).reshape(B, 2)
+        forced = self._a(forced_trace, (B, self.cfg.max_iter, _abi.TRACE_W))
+        fit = self._a(forced_iters, (B,))
+        xe = np.zeros((B, self.H + 1, 13), self.np)
+        trace = np.zeros((B, self.cfg.max_iter, _abi.TRACE_W), self.np)
+        own = np.zeros((B, self.cfg.max_iter, 4), self.np)
+        rc = self._fn("solve_forced")(
+            self._h, C.c_int(B), _ptr(x, self.ct), _ptr(curr_t, self.ct), _ptr(xdes, self.ct), _ptr(xref_win, self.ct),
+            _ptr(rng, C.c_uint64), _ptr(u, self.ct), _ptr(xe, self.ct), _ptr(info, self.ct), _ptr(xi, self.ct),
+            _ptr(trace, self.ct), _ptr(forced, self.ct), _ptr(fit, self.ct), _ptr(own, self.ct))
+        if rc:
+            raise RuntimeError(f"oracle solve_forced failed: {rc}")
+        return u, xe, info, trace, own
+
     def closed_loop(self, x0, t0, rng, ticks, want_hist=True):
         x0 = self._a(x0, (-1, 13))
         R = x0.shape[0]

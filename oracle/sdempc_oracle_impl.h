@@ -644,9 +644,17 @@ typedef struct {
 #define OINFO CAT(oinfo_, SUFFIX)
 
 /* The APG solve of one problem in the internal frame ([SPEC] "APG").
- * plan[H][nu] in/out, xevol[H+1][13] out (internal frame), trace[max_iter][8] or NULL. */
+ * plan[H][nu] in/out, xevol[H+1][13] out (internal frame), trace[max_iter][8] or NULL.
+ *
+ * TEACHER-FORCED mode (forced != NULL; SURVEY.md section 7 "decision-trace teacher-forced mode"): the discrete
+ * decisions of every iteration -- the number of line-search trials and accept / reject -- and the iteration count
+ * are taken from another solver's decision trace `forced[forced_iters][8]` instead of being decided here, so the
+ * sequence of iterates y_k, x_k is the one that solver followed and every continuous quantity (f_y, J_trial, step
+ * size, J_x, |g|^2) can be compared with it at a tolerance although a free-running solve would branch differently
+ * after the first flipped decision.  own[it][4] = (the trial count this oracle would have chosen given the same
+ * trials, its own accept decision, Armijo margin of the last forced trial (>= 0: passes), accept margin J_x - J_trial). */
 static void FN(apg)(const OHANDLE* h, const REAL* x0, const REAL* xref, const REAL* xi, REAL* plan,
-                    REAL* xevol, OINFO* info, REAL* trace, OSTEP* steps) {
+                    REAL* xevol, OINFO* info, REAL* trace, OSTEP* steps, const REAL* forced, int forced_iters, REAL* own) {
     const sdempc_config* c = &h->cfg;
     const OMODEL* m = &h->model;
     const int H = c->horizon, nu = m->nu, n = H * nu;
@@ -670,6 +678,10 @@ static void FN(apg)(const OHANDLE* h, const REAL* x0, const REAL* xref, const RE
         gsq = FN(butterfly)(part);
         if (c->reset_option == 1) { s = s * (REAL)c->increase_factor; s = s > (REAL)c->max_stepsize ? (REAL)c->max_stepsize : s; }
         int ok = 0, n_ls = 0;
+        const REAL* fr = forced ? forced + (size_t)(it - 1) * SDEMPC_TRACE_W : NULL;
+        const int n_forced = fr ? (int)fr[3] : 0;
+        int own_nls = 0;
+        REAL margin_ls = 0;
         for (int j = 0; j <= c->maxls; ++j) {
             for (int l = 0; l < 32; ++l) part[l] = 0;
             for (int i = 0; i < n; ++i) {
@@ -680,11 +692,26 @@ static void FN(apg)(const OHANDLE* h, const REAL* x0, const REAL* xref, const RE
             Jp = FN(rollout)(c, m, x0, xp, uprev, xref, xi, NULL, NULL, steps);
             n_ls = j + 1;
             ok = (Jp <= FMA((REAL)c->coef, dec, fy));
+            margin_ls = FMA((REAL)c->coef, dec, fy) - Jp;
+            if (fr) {   /* teacher forced: evaluate exactly the forced trials, remember where this oracle would have stopped */
+                if (ok && own_nls == 0) own_nls = j + 1;
+                if (j + 1 >= n_forced) break;
+                s = s * (REAL)c->decrease_factor;
+                continue;
+            }
             if (ok) break;
             if (j < c->maxls) s = s * (REAL)c->decrease_factor;
         }
         sum_ls = sum_ls + (REAL)n_ls; sum_s = sum_s + s;
         int accept = ok && (Jp <= Jx), converged = 0;
+        if (fr) {
+            if (own) {
+                REAL* o = own + (size_t)(it - 1) * 4;
+                o[0] = (REAL)(own_nls ? own_nls : (n_forced <= c->maxls ? n_forced + 1 : n_forced));
+                o[1] = (REAL)accept; o[2] = margin_ls; o[3] = Jx - Jp;
+            }
+            accept = fr[4] != 0;
+        }
         if (accept) {
             const REAL beta = (REAL)k / (REAL)(k + 3);
             for (int i = 0; i < n; ++i) {
@@ -703,6 +730,7 @@ static void FN(apg)(const OHANDLE* h, const REAL* x0, const REAL* xref, const RE
             REAL* tr = trace + (size_t)(it - 1) * SDEMPC_TRACE_W;
             tr[0] = fy; tr[1] = Jp; tr[2] = s; tr[3] = (REAL)n_ls; tr[4] = (REAL)accept; tr[5] = Jx; tr[6] = gsq; tr[7] = (REAL)k;
         }
+        if (fr) { if (it >= forced_iters) break; else continue; }
         if (it >= c->max_iter || no_improve >= c->max_no_improvement_iter || converged || !(fy == fy)) break;
     }
     FN(rollout)(c, m, x0, xk, uprev, xref, xi, NULL, xevol, steps);
@@ -838,9 +866,19 @@ int FN(rollout_batch)(void* hv, int B, const REAL* x, const REAL* curr_t, const 
     return rc;
 }
 
-/* batched solve (mirrors sdempc_solve_ex); info[B][8], trace[B][max_iter][8] or NULL */
+/* batched solve (mirrors sdempc_solve_ex); info[B][8], trace[B][max_iter][8] or NULL.
+ * forced[B][max_iter][8] + forced_iters[B] (both or neither): teacher-forced replay of another solver's decision
+ * trace (see apg); own[B][max_iter][4] receives this oracle's own decisions and margins. */
+int FN(solve_forced)(void* hv, int B, const REAL* x, const REAL* curr_t, const REAL* xdes, const REAL* xref_win,
+                     const uint64_t* rng, REAL* u_plan, REAL* x_evol, REAL* info, const REAL* xi_override, REAL* trace,
+                     const REAL* forced, const REAL* forced_iters, REAL* own);
 int FN(solve)(void* hv, int B, const REAL* x, const REAL* curr_t, const REAL* xdes, const REAL* xref_win,
               const uint64_t* rng, REAL* u_plan, REAL* x_evol, REAL* info, const REAL* xi_override, REAL* trace) {
+    return FN(solve_forced)(hv, B, x, curr_t, xdes, xref_win, rng, u_plan, x_evol, info, xi_override, trace, NULL, NULL, NULL);
+}
+int FN(solve_forced)(void* hv, int B, const REAL* x, const REAL* curr_t, const REAL* xdes, const REAL* xref_win,
+                     const uint64_t* rng, REAL* u_plan, REAL* x_evol, REAL* info, const REAL* xi_override, REAL* trace,
+                     const REAL* forced, const REAL* forced_iters, REAL* own) {
     OHANDLE* h = (OHANDLE*)hv;
     const sdempc_config* c = &h->cfg;
     const int H = c->horizon, nu = c->nu, P = c->num_particles;
@@ -858,8 +896,11 @@ int FN(solve)(void* hv, int B, const REAL* x, const REAL* curr_t, const REAL* xd
             OINFO inf;
             memset(&inf, 0, sizeof(inf));
             inf.stepsize = info[(size_t)b * 8 + 1];
+            const int fi = forced_iters ? (int)forced_iters[b] : 0;
             FN(apg)(h, x0, xref, xi, u_plan + (size_t)b * H * nu, xm, &inf,
-                    trace ? trace + (size_t)b * c->max_iter * SDEMPC_TRACE_W : NULL, steps);
+                    trace ? trace + (size_t)b * c->max_iter * SDEMPC_TRACE_W : NULL, steps,
+                    (forced && fi > 0) ? forced + (size_t)b * c->max_iter * SDEMPC_TRACE_W : NULL, fi,
+                    own ? own + (size_t)b * c->max_iter * 4 : NULL);
             FN(to_ext)(h, xm, x_evol + (size_t)b * (H + 1) * NX, H + 1);
             REAL* o = info + (size_t)b * 8;
             o[0] = inf.avg_linesearch; o[1] = inf.stepsize; o[2] = inf.num_steps; o[3] = inf.grad_sqr;
@@ -903,7 +944,7 @@ int FN(closed_loop)(void* hv, int Rn, int ticks, const REAL* x0s, const REAL* t0
                 if (t < H) tw = tw + (REAL)c->dt[t];
             }
             FN(gen_noise)(seed, tick, P, H, 0, xi);
-            FN(apg)(h, x, xref, xi, plan, xm, &inf, NULL, steps);
+            FN(apg)(h, x, xref, xi, plan, xm, &inf, NULL, steps, NULL, 0, NULL);
             sc = sc + inf.opt_cost; sn = sn + inf.num_steps;
             if (u_hist) for (int i = 0; i < nu; ++i) u_hist[((size_t)r * ticks + k) * nu + i] = plan[i];
             /* plant step */

@@ -75,6 +75,9 @@ struct KParams {
     const float* uprev_in;  // [B][nu]
     float* cost_out;     // [B]
     float* grad_out;     // [B][H][nu] or nullptr
+    // tensor-core solve (mpc_tcsolve.cuh): per-CTA global workspace, problems per CTA, row stride of the workspace arrays
+    float* tcs_ws;
+    int tcs_ppc, tcs_rs;
     // closed loop
     int ticks;
     const float* t0;

@@ -20,7 +20,7 @@
 #include "mpc_group.cuh"
 #include "mpc_kernels.cuh"
 #include "mpc_pcluster.cuh"
-#include "mpc_tc.cuh"
+#include "tc_api.h"
 
 using namespace sdempc;
 
@@ -532,19 +532,6 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
     }
 }
 
-// Tensor-core batched rollout / value_and_grad (mpc_tc.cuh): 128 rows per CTA, thread = (problem, particle) = TMEM lane.
-// Resident CTAs per SM are bounded by tensor memory (512 columns): the register budget is set to allow exactly that many.
-#ifndef SDEMPC_TC_MIN_CTAS
-#define SDEMPC_TC_MIN_CTAS(NU, W) (512 / TCLayout<NU, W>::COLS)
-#endif
-template <int NU, int W, bool GRAD>
-__global__ void __launch_bounds__(128, SDEMPC_TC_MIN_CTAS(NU, W)) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
-    extern __shared__ __align__(1024) unsigned char tc_smem[];
-    __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t tc_bar;
-    tc_rollout_body<NU, W, GRAD>(P, tc_smem, &tmem_slot, &tc_bar);
-}
-
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -582,7 +569,8 @@ struct KernelChoice {
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
-    int tc_bytes, tc_bytes_grad, tc_tape_granules;
+    void (*solve_tc)(KParams);     // tensor-core batched APG solve, SDEMPC_F_TENSOR
+    int tc_bytes, tc_bytes_grad, tc_tape_granules, tc_bytes_solve, tc_solve_tape_granules, tc_cols;
     int gp;
     int nu, W, P, G;
     int wimg_floats, wsmem_floats;
@@ -601,21 +589,12 @@ static KernelChoice make_choice() {
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     k.solve_pc = nullptr;
-    k.rollout_tc = k.rollout_tc_grad = nullptr;
-    k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = 0;
-    {   // one tensor-core kernel per (nu, width): the particle count is a run-time row mapping
-        k.rollout_tc = mpc_tc_rollout_kernel<NU, W, false>;
-        k.rollout_tc_grad = mpc_tc_rollout_kernel<NU, W, true>;
-        // Residency must be bounded by tensor memory (512 / COLS CTAs per SM), never exceed it: a CTA that the block
-        // scheduler places beyond that spins in tcgen05.alloc while holding its slot (width 64, forward variant:
-        // registers and shared memory allowed three CTAs, tensor memory two -- launches were bimodal, 0.30 / 0.41 ms).
-        // Where registers do not already impose the bound, the dynamic shared-memory request is padded so that one
-        // more CTA cannot fit (228 KB per SM, 1 KB reserved per CTA).
-        constexpr int tmem_ctas = 512 / TCLayout<NU, W>::COLS;
-        constexpr int pad = tmem_ctas < 4 ? (228 * 1024) / (tmem_ctas + 1) + 1024 : 0;
-        k.tc_bytes = std::max(TCLayout<NU, W>::BYTES, pad);
-        k.tc_bytes_grad = std::max(TCLayout<NU, W>::BYTES_GRAD, pad);
-        k.tc_tape_granules = TCLayout<NU, W>::TG;
+    k.rollout_tc = k.rollout_tc_grad = k.solve_tc = nullptr;
+    k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
+    if (const TCKernels* t = tc_kernels(NU, W)) {   // one set of tensor-core kernels per (nu, width): the particle count is a run-time row mapping
+        k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve;
+        k.tc_bytes = t->bytes; k.tc_bytes_grad = t->bytes_grad; k.tc_bytes_solve = t->bytes_solve;
+        k.tc_tape_granules = t->tape_granules; k.tc_solve_tape_granules = t->solve_tape_granules; k.tc_cols = t->cols;
     }
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
     k.gp = group_gp(NU, W);
@@ -662,6 +641,8 @@ struct sdempc_handle {
     std::vector<float> wimg_tc;       // tensor-core operand image (TCLayout), forward part then adjoint part
     float* d_wimg_tc = nullptr;
     float* d_tape_tc = nullptr; size_t tape_tc_bytes = 0;
+    float* d_tcs_ws = nullptr; size_t tcs_ws_bytes = 0;   // per-CTA workspaces of the tensor-core solve
+    int tcs_ppc_override = 0;                             // experiments: SDEMPC_TC_PPC
     size_t smem_bytes_group = 0;
     size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
@@ -685,7 +666,7 @@ struct sdempc_handle {
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_tc = false;
     float last_ms = 0.f;
 };
 
@@ -768,6 +749,16 @@ static void pack_weights_tc(sdempc_handle* h) {
 }
 
 static int align4(int v) { return (v + 3) & ~3; }
+
+// host mirror of tcs_ws_layout (mpc_tcsolve.cuh): floats of one CTA's workspace of the tensor-core solve
+struct TCSWsHost { size_t total; };
+static TCSWsHost tcs_ws_floats(int H, int NU, int RS, int TG) {
+    const size_t n = (size_t)H * NU;
+    TCSWsHost w;
+    w.total = 3 * n * RS + (size_t)SDEMPC_MAX_NU * RS + 16 * (size_t)RS + (size_t)(H + 1) * NX * RS + (size_t)H * 6 * 128 +
+              (size_t)H * TG * 128 * 4;
+    return w;
+}
 
 static void build_kparams(sdempc_handle* h) {
     KParams& k = h->kp;
@@ -889,6 +880,7 @@ static int ensure_device(sdempc_handle* h) {
     if (h->kc.rollout_tc) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_grad));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
         CUDA_TRY(cudaMalloc(&h->d_wimg_tc, h->wimg_tc.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_wimg_tc, h->wimg_tc.data(), h->wimg_tc.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -929,6 +921,28 @@ static bool use_group(const sdempc_handle* h, int B) {
     if (h->cfg.flags & SDEMPC_F_GROUP) return true;
     const int per_sm = h->kc.gp == 4 ? 13 : h->kc.gp == 2 ? 10 : (1 << 20);
     return B > per_sm * h->sm_count;
+}
+
+// Tensor-core solve (SDEMPC_F_TENSOR): problems per CTA.  A CTA has 128 / P rollout slots and is latency bound when it
+// is alone on its SM (measured, 4096 iris problems x 200 iterations: 28 problems per CTA on 147 SMs 41 ms; 25 per CTA =
+// the whole line search in one pass but 164 CTAs on 148 SMs 47 ms; 14 per CTA, two CTAs per SM, 45 ms; 7 per CTA 63 ms):
+// spread the batch over the SMs first, one CTA each, and only share an SM between CTAs when the slots are full.
+static int tcs_problems_per_cta(const sdempc_handle* h, int B) {
+    const int P = h->cfg.num_particles, NT = 128 / P;
+    if (h->tcs_ppc_override > 0) return std::min(h->tcs_ppc_override, NT);
+    const int ppc = (B + h->sm_count - 1) / h->sm_count;
+    return std::max(1, std::min(ppc, NT));
+}
+
+static int ensure_tcs_ws(sdempc_handle* h, int grid, int rs) {
+    const TCSWsHost w = tcs_ws_floats(h->cfg.horizon, h->cfg.nu, rs, h->kc.tc_solve_tape_granules);
+    const size_t need = (size_t)grid * w.total * 4;
+    if (need <= h->tcs_ws_bytes) return 0;
+    if (h->d_tcs_ws) cudaFree(h->d_tcs_ws);
+    h->d_tcs_ws = nullptr; h->tcs_ws_bytes = 0;
+    CUDA_TRY(cudaMalloc(&h->d_tcs_ws, need));
+    h->tcs_ws_bytes = need;
+    return 0;
 }
 
 static int ensure_mtape_group(sdempc_handle* h, int grid) {
@@ -1021,12 +1035,18 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     else in_bytes += a16((size_t)B * 16);
     const size_t out_bytes = a16((size_t)B * (H + 1) * NX * 4) + a16((size_t)B * n * 4) + a16((size_t)B * sizeof(sdempc_info)) + 64;
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
-    const bool spec = use_spec(h, B), group = use_group(h, B);
+    // SDEMPC_F_TENSOR: the batched solve on the tensor-core mapping (explicit opt-in: TF32 products, not SPEC-ARITH)
+    const bool tcs = (h->cfg.flags & SDEMPC_F_TENSOR) != 0;
+    if (tcs && (!h->kc.solve_tc || P > 32 || (P & (P - 1)) != 0 || h->cfg.u_slew_constr_coeff != 0.0f))
+        return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core solve supports 1, 2, 4, ... 32 particles and no input-rate constraint");
+    const bool spec = !tcs && use_spec(h, B), group = !tcs && use_group(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
-    const bool cl = use_cluster(h, B), pcl = use_pcluster(h, B);
-    const int grid = pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
+    const bool cl = !tcs && use_cluster(h, B), pcl = !tcs && use_pcluster(h, B);
+    const int ppc = tcs ? tcs_problems_per_cta(h, B) : 0, rs = (ppc + 31) & ~31;
+    const int grid = tcs ? (B + ppc - 1) / ppc : pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
-    if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
+    if (tcs) { if ((rc = ensure_tcs_ws(h, grid, rs))) return rc; }
+    else if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
     else if ((rc = ensure_mtape(h, grid))) return rc;
     if (a->trace) {
         const size_t tb = (size_t)B * h->cfg.max_iter * SDEMPC_TRACE_W * 4;
@@ -1056,7 +1076,9 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
+    if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; }
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl;
+    h->staged_tc = tcs;
     return 0;
 }
 
@@ -1079,12 +1101,18 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
     }
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
-    const int threads = spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
-    const size_t smem = spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
+    const bool tcs = (fn == h->kc.solve_tc) && fn != nullptr;
+    const int threads = tcs ? 128 : spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    const size_t smem = tcs ? (size_t)h->kc.tc_bytes_solve : spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
     void* args[] = {const_cast<KParams*>(&k)};
     CUDA_TRY(cudaLaunchKernel(reinterpret_cast<const void*>(fn), dim3(grid), dim3(threads), args, smem, h->stream));
     h->launches += 1;
     return 0;
+}
+
+static void (*staged_kernel(const sdempc_handle* h))(KParams) {
+    return h->staged_tc ? h->kc.solve_tc : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
+           : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
 static int fetch_solve(sdempc_handle* h, const sdempc_solve_args* a) {
@@ -1135,6 +1163,7 @@ int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbyte
     memcpy(h->weights.data(), (const char*)model_blob + sizeof mh, 2 * per_net * 4);
     pack_weights(h);
     if (h->kc.rollout_tc) pack_weights_tc(h);
+    if (const char* e = getenv("SDEMPC_TC_PPC")) h->tcs_ppc_override = atoi(e);   // experiments: problems per CTA of the tensor-core solve
     build_kparams(h);
     *out = h;
     return 0;
@@ -1146,7 +1175,7 @@ void sdempc_destroy(sdempc_t* h) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
         cudaFree(h->d_wimg); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_mtape_group); cudaFree(h->d_in); cudaFree(h->d_out);
-        cudaFree(h->d_trace); cudaFree(h->d_flush); cudaFree(h->d_wimg_tc); cudaFree(h->d_tape_tc);
+        cudaFree(h->d_trace); cudaFree(h->d_flush); cudaFree(h->d_wimg_tc); cudaFree(h->d_tape_tc); cudaFree(h->d_tcs_ws);
         if (h->h_in) cudaFreeHost(h->h_in);
         if (h->h_out) cudaFreeHost(h->h_out);
         if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1249,7 +1278,7 @@ int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
     for (int i = 0; i < n; ++i) {
         if (flush_l2) CUDA_TRY(cudaMemsetAsync(h->d_flush, i & 0xff, FL, h->stream));
         CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-        int rc = launch(h, h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid);
+        int rc = launch(h, staged_kernel(h), h->staged, h->last_grid);
         if (rc) return rc;
         CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
         CUDA_TRY(cudaEventSynchronize(h->ev1));
@@ -1290,7 +1319,7 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     int rc = stage_solve(h, a);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = launch(h, h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec : h->staged_group ? h->kc.solve_group : h->kc.solve, h->staged, h->last_grid))) return rc;
+    if ((rc = launch(h, staged_kernel(h), h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
     if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
     float t = 0.f;
@@ -1432,6 +1461,10 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
+    if (h->staged_tc) {
+        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->regs; out[4] = h->last_grid; out[5] = h->sm_count;
+        return 0;
+    }
     out[0] = (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
     out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * h->kc.gp : h->kc.G;

@@ -269,3 +269,35 @@ def test_oracle_reproduces_golden_vectors():
         out = make_golden.run_case(case, backend="oracle")
         for k, v in out.items():
             assert np.array_equal(v, z[f"{case['name']}/{k}"]), (case["name"], k)
+
+
+def test_teacher_forced_mode_replays_a_decision_trace():
+    """TEACHER-FORCED mode: forcing the oracle with its own decision trace reproduces the free
+    solve bit for bit; forcing the float64 oracle with the float32 trace keeps the two on the same sequence of
+    iterates, so early iterations agree to rounding, `own` reports the decisions it would have taken itself, and
+    a deliberately wrong decision is followed, not corrected."""
+    cfg, blob, _ = make_setup("iris", "traj", max_iter=40, rtol=0.0, atol=0.0)
+    o32, o64 = O.Oracle(cfg, blob, "f32"), O.Oracle(cfg, blob, "f64")
+    B = 12
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=2)
+    u0, i0 = o32.reset(B)
+    kw = dict(xref_win=pr["xref_win"], rng=pr["rng"])
+    a = o32.solve(pr["x"], u0, i0, want_trace=True, **kw)
+    f = o32.solve_forced(pr["x"], u0, i0, a[3], a[2][:, 2], **kw)
+    assert np.array_equal(f[0], a[0]) and np.array_equal(f[1], a[1]) and np.array_equal(f[3], a[3]) and np.array_equal(f[2][:, :7], a[2][:, :7])
+    assert np.array_equal(f[4][:, :, 0], a[3][:, :, 3]) and np.array_equal(f[4][:, :, 1], a[3][:, :, 4]), "own decisions == forced decisions"
+    acc = a[3][:, :, 4] > 0
+    assert np.all(f[4][:, :, 2][acc] >= 0) and np.all(f[4][:, :, 3][acc] >= 0), "margins of accepted steps are non-negative"
+    g = o64.solve_forced(pr["x"], u0, i0, a[3], a[2][:, 2], **kw)
+    rel = np.abs(g[3][:, :10, [0, 5]] - a[3][:, :10, [0, 5]]) / np.abs(g[3][:, :10, [0, 5]])
+    assert rel.max() <= 2e-5 and np.array_equal(g[3][:, :, 3:5], a[3][:, :, 3:5])
+    # a wrong forced decision (reject the first accepted step of problem 0) is followed
+    tr = a[3].copy()
+    k0 = int(np.argmax(tr[0, :, 4] > 0))
+    tr[0, k0, 4] = 0.0
+    h = o32.solve_forced(pr["x"], u0, i0, tr, a[2][:, 2], **kw)
+    assert h[3][0, k0, 4] == 0.0 and h[4][0, k0, 1] == 1.0 and h[3][0, k0, 7] == 1.0
+    assert np.array_equal(h[0][1:], a[0][1:]) and not np.array_equal(h[0][0], a[0][0])
+    # fewer forced iterations than max_iter: stops there
+    short = o32.solve_forced(pr["x"], u0, i0, a[3], np.full(B, 7.0), **kw)
+    assert np.all(short[2][:, 2] == 7) and np.array_equal(short[3][:, :7], a[3][:, :7])
