@@ -231,6 +231,11 @@ int64_t sdempc_launch_count(const sdempc_t* h);
  * out[3]=registers per thread, out[4]=CTAs launched last time, out[5]=SM count. */
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]);
 
+/* Measurement aid (no reference counterpart): what the FP32 FMA pipe of `device` sustains right now, in TFLOP/s
+ * (an FFMA-bound kernel, 16 warps per SM, best of three launches, CUDA-event timed).  bench.py uses it as the
+ * denominator of the FP32 roofline, measured in the same run as the solve. */
+int sdempc_probe_fp32(int device, float* tflops);
+
 void sdempc_destroy(sdempc_t* h);
 const char* sdempc_last_error(void);
 const char* sdempc_version(void);

@@ -86,7 +86,7 @@ class SolveArgs(C.Structure):
 HEADER_SYMBOLS = [
     "sdempc_create", "sdempc_set_trajectory", "sdempc_state_from_traj", "sdempc_reset",
     "sdempc_solve_ex", "sdempc_solve", "sdempc_rollout", "sdempc_closed_loop", "sdempc_stage",
-    "sdempc_launch_timed", "sdempc_sync", "sdempc_device_out", "sdempc_fetch", "sdempc_launch_count", "sdempc_last_launch_ms", "sdempc_kernel_info",
+    "sdempc_launch_timed", "sdempc_sync", "sdempc_device_out", "sdempc_fetch", "sdempc_launch_count", "sdempc_last_launch_ms", "sdempc_kernel_info", "sdempc_probe_fp32",
     "sdempc_destroy", "sdempc_last_error", "sdempc_version",
 ]
 
@@ -131,6 +131,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.sdempc_last_launch_ms.argtypes = [vp]
     lib.sdempc_last_launch_ms.restype = C.c_float
     lib.sdempc_kernel_info.argtypes = [vp, C.POINTER(_i * 6)]
+    lib.sdempc_probe_fp32.argtypes = [C.c_int, _fp]
     lib.sdempc_destroy.argtypes = [vp]
     lib.sdempc_destroy.restype = None
     lib.sdempc_last_error.restype = C.c_char_p

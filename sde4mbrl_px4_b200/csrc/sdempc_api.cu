@@ -532,6 +532,24 @@ __global__ void __launch_bounds__(GW * 32, 1) mpc_group_kernel(const __grid_cons
     }
 }
 
+// FP32-pipe probe: 8 independent FFMA chains per thread, 16 warps per SM (4 per sub-partition).  The roofline
+// denominator of bench.py: what the FMA pipe of THIS device sustains at the clocks it runs at, measured in the same run.
+__global__ void __launch_bounds__(512, 1) fp32_probe_kernel(float* out, int iters) {
+    float a[8], b[8], c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[i] = 1.0f + threadIdx.x * 1e-6f + i; b[i] = 0.999f + i * 1e-7f; c[i] = 0.5f * i; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) c[i] = __fmaf_rn(a[i], b[i], c[i]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -1453,6 +1471,36 @@ int sdempc_closed_loop(sdempc_t* h, int R, int ticks, const float* x0, const flo
     memcpy(stats, h->h_out + off, (size_t)R * 16); off += a16((size_t)R * 16);
     if (x_hist) { memcpy(x_hist, h->h_out + off, (size_t)R * (ticks + 1) * NX * 4); off += xh; }
     if (u_hist) { memcpy(u_hist, h->h_out + off, (size_t)R * ticks * NU * 4); off += uh; }
+    return 0;
+}
+
+int sdempc_probe_fp32(int device, float* tflops) {
+    if (!tflops) return fail(SDEMPC_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(SDEMPC_ECUDA, "no usable CUDA device %d", device);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int grid = prop.multiProcessorCount, threads = 512, iters = 20000;
+    float* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)grid * threads * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {   // first launch warms the clocks up; best of the rest
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        fp32_probe_kernel<<<grid, threads>>>(d, iters);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    CUDA_TRY(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    const double flop = 2.0 * 64.0 * iters * (double)grid * threads;
+    *tflops = (float)(flop / (best * 1e-3) / 1e12);
     return 0;
 }
 

@@ -25,6 +25,16 @@ def _f32(a, shape=None):
     return a.reshape(shape) if shape is not None else a
 
 
+def probe_fp32_tflops(device: int = 0) -> float:
+    """FP32 FMA-pipe throughput of ``device`` measured now (``sdempc_probe_fp32``): the roofline denominator."""
+    v = C.c_float(0.0)
+    lib = _abi.load_library()
+    rc = lib.sdempc_probe_fp32(device, C.byref(v))
+    if rc != 0:
+        raise RuntimeError(f"sdempc error {rc}: {lib.sdempc_last_error().decode()}")
+    return float(v.value)
+
+
 class MPCSolver:
     def __init__(self, cfg: _abi.Config, model_blob: bytes, device: int = 0, lib_path: str | None = None):
         self.lib = _abi.load_library(lib_path)
