@@ -91,7 +91,7 @@ typedef struct sdempc_config {
     float u_slew_coeff;              /* yaml:41 */
     float init_stepsize, max_stepsize, coef, decrease_factor, increase_factor; /* yaml:76-80 */
     float atol, rtol;                /* yaml:72-73 */
-    float beta_init;                 /* yaml:69 (informational: beta_1 = 1/4 = k/(k+3))    */
+    float beta_init;                 /* yaml:69: initial momentum of the adaptive rule (moment_scale); the classical rule has beta_1 = 1/4 */
     /* Soft input-rate constraint of the position-control configuration
      * (cost_params.u_slew_constr / u_slew_constr_coeff, iris_sitl_posctrl_mpc.yaml:40-41): with
      * ds = u_t[i] - u_{t-1}[i] and e = ds - hi (ds > hi), ds - lo (ds < lo), 0 otherwise, every stage adds
@@ -99,6 +99,11 @@ typedef struct sdempc_config {
     float u_slew_constr_coeff;
     float u_slew_lo[SDEMPC_MAX_NU];
     float u_slew_hi[SDEMPC_MAX_NU];
+    /* apg_mpc.moment_scale (yaml:63-66: "the adaptive coefficient to scale the momentum ... between 0 and 1"; null = the
+     * classical beta_k = k / (k + 3)).  0 = null.  [SPEC] for mu in (0, 1]: the momentum starts at beta_init (yaml:69) after a
+     * reset or a rejected step and is scaled by 1 / mu at every accepted step, capped at 1:
+     * beta_k = min(1, beta_init / mu^(k-1)), k = accepted steps since the last restart + 1 (mu = 1: constant momentum). */
+    float moment_scale;
 } sdempc_config;
 
 /*

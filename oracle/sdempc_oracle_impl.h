@@ -713,7 +713,11 @@ static void FN(apg)(const OHANDLE* h, const REAL* x0, const REAL* xref, const RE
             accept = fr[4] != 0;
         }
         if (accept) {
-            const REAL beta = (REAL)k / (REAL)(k + 3);
+            REAL beta = (REAL)k / (REAL)(k + 3);
+            if (c->moment_scale != 0.0f) {   /* [SPEC] adaptive momentum: beta_init scaled by 1 / moment_scale per accepted step, capped at 1 */
+                beta = (REAL)c->beta_init;
+                for (int i = 1; i < k && beta < (REAL)1; ++i) { beta = beta / (REAL)c->moment_scale; beta = beta > (REAL)1 ? (REAL)1 : beta; }
+            }
             for (int i = 0; i < n; ++i) {
                 yk[i] = FN(clip)(FMA(beta, xp[i] - xk[i], xp[i]), (REAL)c->u_lo[i % nu], (REAL)c->u_hi[i % nu]);
                 xk[i] = xp[i];

@@ -44,6 +44,7 @@ class Config(C.Structure):
         ("init_stepsize", _f), ("max_stepsize", _f), ("coef", _f), ("decrease_factor", _f),
         ("increase_factor", _f), ("atol", _f), ("rtol", _f), ("beta_init", _f),
         ("u_slew_constr_coeff", _f), ("u_slew_lo", _f * MAX_NU), ("u_slew_hi", _f * MAX_NU),
+        ("moment_scale", _f),
     ]
 
 

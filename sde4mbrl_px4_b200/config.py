@@ -90,14 +90,15 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
     bounds = ic["input_bound"]
     if len(bounds) != nu:
         raise ConfigError("input_constr.input_bound must have one [lo, hi] pair per input")
-    if not cfg.get("enforce_ubound", True):
-        warnings.warn("enforce_ubound: False is not supported; the input box is always enforced by projection")
+    enforce = bool(cfg.get("enforce_ubound", True))   # yaml:14; False: the box is not projected onto (bounds +-FLT_MAX)
     cp = cfg["cost_params"]
     uref = list(cp["uref"])
     if len(uref) != nu:
         raise ConfigError("cost_params.uref must have nu entries")
     for i in range(nu):
         c.u_lo[i], c.u_hi[i], c.uref[i] = float(bounds[i][0]), float(bounds[i][1]), float(uref[i])
+        if not enforce:
+            c.u_lo[i], c.u_hi[i] = -3.0e38, 3.0e38
     c.uerr = float(cp.get("uerr", 0.0))
 
     def vec3(key):
@@ -130,16 +131,19 @@ def build_config(cfg: dict, convert_to_enu: bool = True, strict: bool = False, *
     c.atol = float(overrides.get("atol", apg.get("atol", 0.0)))
     c.rtol = float(overrides.get("rtol", apg.get("rtol", 0.0)))
     c.beta_init = float(apg.get("beta_init", 0.25))
-    if c.beta_init != 0.25:
+    ms = apg.get("moment_scale", None)
+    c.moment_scale = 0.0 if ms is None else float(ms)
+    if ms is not None and not 0.0 < float(ms) <= 1.0:
+        raise ConfigError("apg_mpc.moment_scale must be null or in (0, 1] (launch/iris_sitl_traj_mpc.yaml:63-66)")
+    if ms is None and c.beta_init != 0.25:
         # the momentum rule is beta_k = k / (k + 3) (launch/iris_sitl_traj_mpc.yaml:63-66), whose first value is 1/4
-        msg = f"apg_mpc.beta_init = {c.beta_init} is not applied: the solver uses beta_k = k / (k + 3) (beta_1 = 0.25)"
+        msg = (f"apg_mpc.beta_init = {c.beta_init} is not applied while moment_scale is null: the classical momentum is "
+               "beta_k = k / (k + 3) (beta_1 = 0.25)")
         if strict:
             raise ConfigError(msg)
         warnings.warn(msg)
 
     unsupported = [k for k in _UNSUPPORTED_COST_KEYS if k in cp] + [k for k in _UNSUPPORTED_TOP_KEYS if k in cfg]
-    if apg.get("moment_scale", None) is not None:
-        unsupported.append("apg_mpc.moment_scale")
     if unsupported:
         msg = f"config keys parsed but not applied by this solver: {unsupported} (see DESIGN.md, out of scope)"
         if strict:

@@ -227,7 +227,7 @@ __device__ __forceinline__ void g_apg_solve(const KParams& P, Warp<NU, W>& c, co
                 // ---- line search finished for every problem of this iteration: accept / reject ----
                 if (active) { sum_ls = sum_ls + (float)n_ls; sum_s = sum_s + s; }
                 const bool accept = active && ok && (Jp <= Jx);
-                const float beta = __fdiv_rn((float)k, (float)(k + 3));
+                const float beta = apg_momentum(P, k);
                 for (unsigned m = am; m; m &= m - 1) {
                     const int b = __ffs(m) - 1;
                     float* rb = gw.reg(b);

@@ -44,6 +44,7 @@ struct KParams {
     float slewc, slew_lo[SDEMPC_MAX_NU], slew_hi[SDEMPC_MAX_NU];   // soft rate constraint (0: off)
     float rate_w[SDEMPC_MAX_H];                                    // slewc * discount^t (float products, host)
     float init_step, max_step, coef, dec_f, inc_f, atol, rtol;
+    float moment_scale, beta_init;                                 // adaptive momentum (0: classical k / (k + 3))
     // rigid-body model
     float inv_m, grav, kT, kT2, J[3], Jinv[3], Jd[3], mixer[3][SDEMPC_MAX_NU], sig0[6];
     // device data
@@ -77,7 +78,7 @@ struct KParams {
     float* grad_out;     // [B][H][nu] or nullptr
     // tensor-core solve (mpc_tcsolve.cuh): per-CTA global workspace, problems per CTA, row stride of the workspace arrays
     float* tcs_ws;
-    int tcs_ppc, tcs_rs;
+    int tcs_ppc, tcs_rs, tcs_sms;
     // closed loop
     int ticks;
     const float* t0;
@@ -131,6 +132,14 @@ __device__ __forceinline__ float2 lds2(const float* p) { return *reinterpret_cas
 __device__ __forceinline__ float2 xy(float4 v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 zw(float4 v) { return make_float2(v.z, v.w); }
 __device__ __forceinline__ float clipf(float v, float lo, float hi) { v = v < lo ? lo : v; return v > hi ? hi : v; }
+
+// momentum of the k-th consecutive accepted step ([SPEC] "APG" step 4; include/sdempc.h `moment_scale`)
+__device__ __forceinline__ float apg_momentum(const KParams& P, int k) {
+    if (P.moment_scale == 0.f) return __fdiv_rn((float)k, (float)(k + 3));
+    float b = P.beta_init;
+    for (int i = 1; i < k && b < 1.0f; ++i) { b = __fdiv_rn(b, P.moment_scale); b = b > 1.0f ? 1.0f : b; }
+    return b;
+}
 
 // warp-shaped sum of SPEC-ARITH: per-lane strided partial, then xor butterfly 16,8,4,2,1
 __device__ __forceinline__ float warp_butterfly(float p) {
@@ -1020,7 +1029,7 @@ __device__ __forceinline__ void apg_solve(const KParams& P, Warp<NU, W>& c, cons
         const bool accept = ok && (Jp <= Jx);
         bool converged = false;
         if (accept) {
-            const float beta = __fdiv_rn((float)k, (float)(k + 3));
+            const float beta = apg_momentum(P, k);
             for (int i = lane; i < n; i += 32) {
                 const int ii = i % NU;
                 const float xv = c.xp[i];
@@ -1100,7 +1109,7 @@ __device__ __forceinline__ void apg_solve_latency(const KParams& P, Warp<NU, W>&
         }
         if (P.reset_option == 1) { s = s * P.inc_f; s = s > P.max_step ? P.max_step : s; }
         const float s0 = s;
-        const float beta = __fdiv_rn((float)k, (float)(k + 3));
+        const float beta = apg_momentum(P, k);
         // ---- speculation warps: value_and_grad at the candidate next point, into g2 ----
         bool spec_valid = false;
         if (SGW > 0 && is_spec) {

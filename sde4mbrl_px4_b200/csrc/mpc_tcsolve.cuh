@@ -27,7 +27,10 @@
 
 namespace sdempc {
 
-// per-CTA workspace, float offsets; problem-indexed arrays have row stride RS (a multiple of 32)
+// per-CTA workspace, float offsets; problem-indexed arrays have the constant row stride TCS_RS = 128 (one slot per
+// possible problem of a CTA), so that every access is base + compile-time offset (with a run-time stride a quarter of the
+// kernel's instructions were address arithmetic); rows beyond the CTA's problems are never touched
+constexpr int TCS_RS = 128;
 struct TCSWs {
     int RS, n, o_xk, o_yk, o_g, o_uprev, o_x0, o_xref, o_xi, o_tape, total;
 };
@@ -146,7 +149,12 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
     float* XI = wsb + ws.o_xi;
     float4* tape = reinterpret_cast<float4*>(wsb + ws.o_tape) + tid;
     auto tp = [&](int t, int g) -> float4* { return tape + ((size_t)t * L::STG + g) * 128; };
-    const int RS = ws.RS, n = ws.n;
+    // the tape is written once and read once per iteration: streaming stores / loads (evict first), so that it does not
+    // push the plans, the reference window and the noise of the resident CTAs out of L2
+    const bool lone_cta = gridDim.x <= (unsigned)P.tcs_sms;   // one CTA per SM: the next step's tape fits L1, prefetch that far
+    auto stt = [&](int t, int g, float4 v) { if (lone_cta) *tp(t, g) = v; else __stcs(tp(t, g), v); };
+    constexpr int RS = TCS_RS;
+    const int n = ws.n;
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
     const float invP = __fdiv_rn(1.0f, (float)PP);
     const int pbase = lane & ~(PP - 1);
@@ -247,22 +255,42 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     sh.acc[tid] = (sh.ok[tid] && (Jp <= sh.Jx[tid])) ? 1 : 0;
                 } else if (tid < 128) sh.acc[tid] = 2;     // 2: not an active problem, plans untouched
                 __syncthreads();
-                // plans: every thread updates a strided share of the (entry, problem) pairs (coalesced over problems)
-                for (int idx = tid; idx < n * nq; idx += 128) {
-                    const int i = idx / nq, oq = idx - i * nq;
-                    const int a = sh.acc[oq];
-                    if (a == 2) continue;
-                    const int ii = i % NU;
-                    const float xkv = XK[i * RS + oq];
-                    if (a == 1) {
+                // plans: thread -> (problem oq = tid mod 2^k, part): consecutive threads touch consecutive problems (coalesced),
+                // a problem's entries are split over 128 / 2^k threads; four independent entries are in flight per thread
+                {
+                    int npad = 1;
+                    while (npad < nq) npad <<= 1;
+                    const int oq = tid & (npad - 1), part = tid / npad, nparts = 128 / npad;
+                    const int a = oq < nq ? (int)sh.acc[oq] : 2;
+                    if (a != 2) {
+                        const float sq = sh.s[oq];
                         const int kq = sh.k[oq];
-                        const float beta = __fdiv_rn((float)kq, (float)(kq + 3));
-                        const float yv = YK[i * RS + oq];
-                        const float xv = clipf(fma_(-sh.s[oq], G[i * RS + oq], yv), P.u_lo[ii], P.u_hi[ii]);
-                        YK[i * RS + oq] = clipf(fma_(beta, xv - xkv, xv), P.u_lo[ii], P.u_hi[ii]);
-                        XK[i * RS + oq] = xv;
-                    } else {
-                        YK[i * RS + oq] = xkv;
+                        const float beta = apg_momentum(P, kq);
+                        for (int i0 = part; i0 < n; i0 += 4 * nparts) {
+                            float xkv[4], yv[4], gv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int i = i0 + j * nparts;
+                                if (i < n) {
+                                    xkv[j] = XK[i * RS + oq];
+                                    if (a == 1) { yv[j] = YK[i * RS + oq]; gv[j] = G[i * RS + oq]; }
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int i = i0 + j * nparts;
+                                if (i < n) {
+                                    const int ii = i % NU;
+                                    if (a == 1) {
+                                        const float xv = clipf(fma_(-sq, gv[j], yv[j]), P.u_lo[ii], P.u_hi[ii]);
+                                        YK[i * RS + oq] = clipf(fma_(beta, xv - xkv[j], xv), P.u_lo[ii], P.u_hi[ii]);
+                                        XK[i * RS + oq] = xv;
+                                    } else {
+                                        YK[i * RS + oq] = xkv[j];
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
                 __syncthreads();   // sh.k is read above, updated below
@@ -346,12 +374,20 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             for (int i = 0; i < NX; ++i) P.x_evol[(size_t)b * (P.H + 1) * NX + i] = __ldg(P.x + (size_t)b * NX + i);
         }
         float Jp = 0.f, disc = 1.f, dec = 0.f;
+        const float* yq = useq + q;
+        const float* gq = G + q;
+        const float* xiq = XI + xi_row;
+        const float* xrq = XREF + q;
         for (int t = 0; t < P.H; ++t) {
+            const float* yt = yq + t * (NU * RS);
+            const float* gt = gq + t * (NU * RS);
+            const float* xit = xiq + t * (6 * 128);
+            const float* xrt = xrq + (t + 1) * (NX * RS);
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
-                const float yv = useq[(t * NU + i) * RS + q];
+                const float yv = yt[i * RS];
                 if (mode == 0) {
-                    const float gv = G[(t * NU + i) * RS + q];
+                    const float gv = gt[i * RS];
                     const float xv = clipf(fma_(-s_t, gv, yv), P.u_lo[i], P.u_hi[i]);
                     dec = fma_(gv, xv - yv, dec);
                     u[i] = xv;
@@ -361,19 +397,19 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             }
             float xi[6], xr[NX];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) xi[i] = XI[(t * 6 + i) * 128 + xi_row];
+            for (int i = 0; i < 6; ++i) xi[i] = xit[i * 128];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) xr[i] = XREF[((t + 1) * NX + i) * RS + q];
-            if (t + 1 < P.H) {   // next step's operands towards L1 while this step's contractions run
+            for (int i = 0; i < NX; ++i) xr[i] = xrt[i * RS];
+            if (lone_cta && t + 1 < P.H) {   // next step's operands towards L1 while this step's contractions run (CTA alone on its SM)
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
-                    tc::prefetch_l1(useq + ((t + 1) * NU + i) * RS + q);
-                    if (mode == 0) tc::prefetch_l1(G + ((t + 1) * NU + i) * RS + q);
+                    tc::prefetch_l1(yt + (NU + i) * RS);
+                    if (mode == 0) tc::prefetch_l1(gt + (NU + i) * RS);
                 }
 #pragma unroll
-                for (int i = 0; i < 6; ++i) tc::prefetch_l1(XI + ((t + 1) * 6 + i) * 128 + xi_row);
+                for (int i = 0; i < 6; ++i) tc::prefetch_l1(xit + (6 + i) * 128);
 #pragma unroll
-                for (int i = 0; i < NX; ++i) tc::prefetch_l1(XREF + ((t + 2) * NX + i) * RS + q);
+                for (int i = 0; i < NX; ++i) tc::prefetch_l1(xrt + (NX + i) * RS);
             }
             // ---- layer 1 operand: [z, 1, 0 ...] ----
             {
@@ -403,8 +439,8 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                 for (int i = 0; i < 16; ++i) v[i] = tc::tanh_approx(v[i]);
                 tc::st16(lane_addr + L::C_A + c0, v);
                 if (mode == 1 && valid) {
-                    *tp(t, L::S_H1 + c0 / 8) = tc::pack8(v);
-                    *tp(t, L::S_H1 + c0 / 8 + 1) = tc::pack8(v + 8);
+                    stt(t, L::S_H1 + c0 / 8, tc::pack8(v));
+                    stt(t, L::S_H1 + c0 / 8 + 1, tc::pack8(v + 8));
                 }
             }
             tc::publish();
@@ -430,8 +466,8 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                 }
                 tc::st16(lane_addr + L::C_A + c0, v);
                 if (mode == 1 && valid) {
-                    *tp(t, L::S_H2 + c0 / 8) = tc::pack8(v);
-                    *tp(t, L::S_H2 + c0 / 8 + 1) = tc::pack8(v + 8);
+                    stt(t, L::S_H2 + c0 / 8, tc::pack8(v));
+                    stt(t, L::S_H2 + c0 / 8 + 1, tc::pack8(v + 8));
                 }
             }
             tc::publish();
@@ -458,14 +494,14 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             float xn[NX], rn;
             const float l = phys_step<NU>(P, t, x, u, up, r6, sig, xi, xr, xn, rn);
             if (mode == 1 && valid) {
-                *tp(t, L::S_ST) = make_float4(r6[0], r6[1], r6[2], sig[0]);
-                *tp(t, L::S_ST + 1) = make_float4(sig[1], sig[2], sig[3], sig[4]);
-                *tp(t, L::S_ST + 2) = make_float4(sig[5], dsg[0], dsg[1], dsg[2]);
-                *tp(t, L::S_ST + 3) = make_float4(dsg[3], dsg[4], dsg[5], rn);
-                *tp(t, L::S_ST + 4) = make_float4(disc, x[0], x[1], x[2]);          // x is still x_t here
-                *tp(t, L::S_ST + 5) = make_float4(x[3], x[4], x[5], x[6]);
-                *tp(t, L::S_ST + 6) = make_float4(x[7], x[8], x[9], x[10]);
-                *tp(t, L::S_ST + 7) = make_float4(x[11], x[12], 0.f, 0.f);
+                stt(t, L::S_ST, make_float4(r6[0], r6[1], r6[2], sig[0]));
+                stt(t, L::S_ST + 1, make_float4(sig[1], sig[2], sig[3], sig[4]));
+                stt(t, L::S_ST + 2, make_float4(sig[5], dsg[0], dsg[1], dsg[2]));
+                stt(t, L::S_ST + 3, make_float4(dsg[3], dsg[4], dsg[5], rn));
+                stt(t, L::S_ST + 4, make_float4(disc, x[0], x[1], x[2]));          // x is still x_t here
+                stt(t, L::S_ST + 5, make_float4(x[3], x[4], x[5], x[6]));
+                stt(t, L::S_ST + 6, make_float4(x[7], x[8], x[9], x[10]));
+                stt(t, L::S_ST + 7, make_float4(x[11], x[12], 0.f, 0.f));
             }
             Jp = fma_(disc, l, Jp);
             disc = disc * P.discount;
@@ -524,11 +560,11 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
 #pragma unroll
             for (int i = 0; i < NU; ++i) gp[i] = 0.f;
             float gsq = 0.f;
-            auto ldt = [&](int t, int g) -> float4 { return valid ? *tp(t, g) : make_float4(0.f, 0.f, 0.f, 0.f); };
+            auto ldt = [&](int t, int g) -> float4 { return !valid ? make_float4(0.f, 0.f, 0.f, 0.f) : lone_cta ? *tp(t, g) : __ldcs(tp(t, g)); };
             for (int t = P.H - 1; t >= 0; --t) {
                 if (t > 0 && valid) {   // the sweep consumes its tape as it loads it: pull the previous step's granules towards the SM now
 #pragma unroll
-                    for (int g = 0; g < L::STG; ++g) tc::prefetch_l1(tp(t - 1, g));
+                    for (int g = 0; g < L::STG; ++g) { if (lone_cta) tc::prefetch_l1(tp(t - 1, g)); else tc::prefetch_l2(tp(t - 1, g)); }
                 }
                 float xt[NX], xi[6], xr[NX];
                 const float4 s0 = ldt(t, L::S_ST), s1 = ldt(t, L::S_ST + 1), s2 = ldt(t, L::S_ST + 2), s3 = ldt(t, L::S_ST + 3),
@@ -538,14 +574,20 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     xt[0] = s4.y; xt[1] = s4.z; xt[2] = s4.w; xt[3] = c5.x; xt[4] = c5.y; xt[5] = c5.z; xt[6] = c5.w;
                     xt[7] = c6.x; xt[8] = c6.y; xt[9] = c6.z; xt[10] = c6.w; xt[11] = c7.x; xt[12] = c7.y;
                 }
+                {
+                    const float* xit = XI + xi_row + t * (6 * 128);
+                    const float* xrt = XREF + q + (t + 1) * (NX * RS);
+                    const float* yt = YK + q + t * (NU * RS);
+                    const float* ypt = (t == 0) ? UPREV + q : yt - NU * RS;
 #pragma unroll
-                for (int i = 0; i < 6; ++i) xi[i] = XI[(t * 6 + i) * 128 + xi_row];
+                    for (int i = 0; i < 6; ++i) xi[i] = xit[i * 128];
 #pragma unroll
-                for (int i = 0; i < NX; ++i) xr[i] = XREF[((t + 1) * NX + i) * RS + q];
+                    for (int i = 0; i < NX; ++i) xr[i] = xrt[i * RS];
 #pragma unroll
-                for (int i = 0; i < NU; ++i) u[i] = YK[(t * NU + i) * RS + q];
+                    for (int i = 0; i < NU; ++i) u[i] = yt[i * RS];
 #pragma unroll
-                for (int i = 0; i < NU; ++i) up[i] = (t == 0) ? UPREV[i * RS + q] : YK[((t - 1) * NU + i) * RS + q];
+                    for (int i = 0; i < NU; ++i) up[i] = ypt[i * RS];
+                }
                 BwdMid mid;
                 float gu[NU];
                 float2 lo[6];
@@ -637,7 +679,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                 for (int i = 0; i < NU; ++i) {
                     const float gm = pmean(gu[i]);
                     gsq = fma_(gm, gm, gsq);
-                    if (valid && pidx == 0) G[(t * NU + i) * RS + q] = gm;
+                    if (valid && pidx == 0) G[q + t * (NU * RS) + i * RS] = gm;
                 }
 #pragma unroll
                 for (int i = 0; i < NX; ++i) xn[i] = xt[i];

@@ -799,6 +799,7 @@ static void build_kparams(sdempc_handle* h) {
     for (int i = 0; i < SDEMPC_MAX_NU; ++i) { k.slew_lo[i] = c.u_slew_lo[i]; k.slew_hi[i] = c.u_slew_hi[i]; }
     k.init_step = c.init_stepsize; k.max_step = c.max_stepsize; k.coef = c.coef; k.dec_f = c.decrease_factor;
     k.inc_f = c.increase_factor; k.atol = c.atol; k.rtol = c.rtol;
+    k.moment_scale = c.moment_scale; k.beta_init = c.beta_init;
     // derived model constants: one IEEE float operation each (the oracle derives them identically)
     k.inv_m = 1.0f / m.mass; k.grav = m.gravity; k.kT = m.k_thrust; k.kT2 = 2.0f * m.k_thrust;
     for (int i = 0; i < 3; ++i) { k.J[i] = m.inertia[i]; k.Jinv[i] = 1.0f / m.inertia[i]; }
@@ -1060,7 +1061,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     const bool spec = !tcs && use_spec(h, B), group = !tcs && use_group(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
     const bool cl = !tcs && use_cluster(h, B), pcl = !tcs && use_pcluster(h, B);
-    const int ppc = tcs ? tcs_problems_per_cta(h, B) : 0, rs = (ppc + 31) & ~31;
+    const int ppc = tcs ? tcs_problems_per_cta(h, B) : 0, rs = 128;   // TCS_RS (mpc_tcsolve.cuh)
     const int grid = tcs ? (B + ppc - 1) / ppc : pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
     if (tcs) { if ((rc = ensure_tcs_ws(h, grid, rs))) return rc; }
@@ -1094,7 +1095,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.info_out = po.reserve<sdempc_info>((size_t)B);
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
-    if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; }
+    if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; k.tcs_sms = h->sm_count; }
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl;
     h->staged_tc = tcs;
     return 0;
@@ -1166,6 +1167,8 @@ int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbyte
     // the kernels build the reference window and write x_evol with one lane per row (rows 0..H): H + 1 <= 32
     if (cfg->horizon < 1 || cfg->horizon > SDEMPC_MAX_H - 1) return fail(SDEMPC_EINVAL, "horizon out of range 1..%d", SDEMPC_MAX_H - 1);
     if (cfg->max_iter < 1 || cfg->maxls < 0) return fail(SDEMPC_EINVAL, "max_iter must be >= 1 and maxls >= 0");
+    if (!(cfg->moment_scale >= 0.f && cfg->moment_scale <= 1.f) || (cfg->moment_scale > 0.f && !(cfg->beta_init >= 0.f && cfg->beta_init <= 1.f)))
+        return fail(SDEMPC_EINVAL, "moment_scale must be 0 (classical momentum) or in (0, 1], with beta_init in [0, 1]");
     const int W = mh.width, NIN = mh.n_in;
     const size_t per_net = (size_t)W * NIN + W + (size_t)W * W + W + 6 * (size_t)W + 6;
     if (nbytes < sizeof mh + 2 * per_net * 4) return fail(SDEMPC_EINVAL, "model blob truncated");

@@ -115,17 +115,54 @@ def gather_to_rank0(parts: dict, bufs: dict | None = None) -> dict | None:
     return out if rank == 0 else None
 
 
-def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
-    """One batched solve of this rank's shard followed by the final result gather **device to device**:
-    inputs go host -> HBM (pinned staging), the solve kernel runs, every rank's OUT block (x_evol | plan |
-    telemetry) is sent over NCCL / NVLink straight from the library's device buffer to rank 0 only (one gather
-    per sub-array, so the gathered arrays are contiguous), and rank 0 copies each array into pinned host memory
-    while the next one is still in flight.  Returns the dict of [B_total, ...] arrays on rank 0 (views of reused
-    pinned buffers), else None.  This is the only collective of the path."""
+class SharedResults:
+    """Final-gather buffers in POSIX shared memory: one segment per result array, laid out [world, B_local, ...], so that
+    every rank copies its OUT block from its own GPU over its own PCIe link straight into its slice and rank 0 reads
+    the concatenated [B_total, ...] arrays without another copy.  Two generations alternate, so the arrays returned by one
+    call stay intact while the next call is being written.  All ranks construct it collectively (one node)."""
+
+    def __init__(self, shapes: dict):
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.shapes, self.gen, self._segs, self.arrays = shapes, 0, [], []
+        for g in range(2):
+            names = [None] * len(shapes)
+            if self.rank == 0:
+                segs = [shared_memory.SharedMemory(create=True, size=max(4, self.world * int(np.prod(sh)) * 4)) for sh in shapes.values()]
+                names = [sg.name for sg in segs]
+            dist.broadcast_object_list(names, src=0)
+            if self.rank != 0:
+                segs = [shared_memory.SharedMemory(name=nm) for nm in names]
+            self._segs.append(segs)
+            self.arrays.append({k: np.ndarray((self.world,) + tuple(sh), np.float32, buffer=sg.buf) for (k, sh), sg in zip(shapes.items(), segs)})
+        dist.barrier()
+        if self.rank == 0:       # the mappings stay valid; the names disappear at once so nothing leaks if a rank dies
+            for segs in self._segs:
+                for sg in segs:
+                    sg.unlink()
+
+    def next(self) -> dict:
+        self.gen ^= 1
+        return self.arrays[self.gen]
+
+
+def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int, gather: str = "shm"):
+    """One batched solve of this rank's shard followed by the final result gather to rank 0, the only exchange of the
+    path ("host concatenation of per-GPU pinned buffers, or one ncclGather"):
+
+    * ``gather="shm"`` (default): every rank copies its OUT block (x_evol | plan | telemetry) device -> host over its own
+      PCIe link into its slice of a shared-memory result array, then one barrier; rank 0 never funnels the other ranks'
+      results through its own link (8 x B200: the gather costs what a single GPU's copy costs);
+    * ``gather="nccl"``: device-to-device gather over NCCL / NVLink straight from the library's OUT block to rank 0 (one
+      gather per sub-array), then rank 0's D2H of all of it, each array's copy overlapped with the next gather.
+
+    Returns the dict of [B_total, ...] arrays on rank 0 (views of reused buffers, valid until the call after next), else None."""
     import torch
     import torch.distributed as dist
 
-    world = dist.get_world_size()
+    world, rank = dist.get_world_size(), dist.get_rank()
     sizes = [shard_range(B_total, r, world)[1] - shard_range(B_total, r, world)[0] for r in range(world)]
     if len(set(sizes)) != 1:
         raise ValueError("solve_sharded needs equal shards (B_total divisible by the world size)")
@@ -133,13 +170,22 @@ def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int):
                  curr_t=local_problem.get("curr_t"), xdes=local_problem.get("xdes"))
     solver.launch_timed(1, flush_l2=False)          # launch + event wait on the handle's stream
     ptr, nbytes, layout = solver.device_out()
-    local = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
-    parts = {k: local[off // 4: off // 4 + int(np.prod(shape))] for k, (off, shape) in layout.items()}
-    key = (world, tuple((k, off, shape) for k, (off, shape) in sorted(layout.items())))
+    key = (gather, world, tuple((k, off, shape) for k, (off, shape) in sorted(layout.items())))
     if _gather_cache.get("key") != key:
         _gather_cache.clear()
         _gather_cache["key"] = key
         _gather_cache["bufs"] = {}
+        if gather == "shm":
+            _gather_cache["shared"] = SharedResults({k: shape for k, (off, shape) in layout.items()})
+    if gather == "shm":
+        arrs = _gather_cache["shared"].next()
+        solver.fetch_into(arrs["u"][rank], arrs["x_evol"][rank], arrs["info"][rank])
+        dist.barrier()
+        if rank != 0:
+            return None
+        return {k: arrs[k].reshape((world * shape[0],) + tuple(shape[1:])) for k, (off, shape) in layout.items()}
+    local = torch.as_tensor(_DevBuf(ptr, nbytes), device="cuda")
+    parts = {k: local[off // 4: off // 4 + int(np.prod(shape))] for k, (off, shape) in layout.items()}
     got = gather_to_rank0(parts, _gather_cache["bufs"])   # ~1.5 KB per problem in total
     if got is None:
         return None

@@ -154,6 +154,19 @@ class MPCSolver:
         self._check(self.lib.sdempc_fetch(self._h, C.byref(a)))
         return keep["u"], keep["xe"], keep["info"]
 
+    def fetch_into(self, u, xe, info):
+        """D2H of the staged solve's outputs straight into caller-provided float32 arrays (e.g. slices of a shared-memory
+        result buffer): u[B,H,nu], xe[B,H+1,13], info[B,8]."""
+        a0, keep = self._staged
+        B = keep["x"].shape[0]
+        for arr, shape in ((u, (B, self.H, self.nu)), (xe, (B, self.H + 1, 13)), (info, (B, 8))):
+            if arr.dtype != np.float32 or tuple(arr.shape) != shape or not arr.flags["C_CONTIGUOUS"]:
+                raise ValueError(f"fetch_into: expected a C-contiguous float32 array of shape {shape}")
+        a = _abi.SolveArgs()
+        C.memmove(C.byref(a), C.byref(a0), C.sizeof(a))
+        a.u_plan, a.x_evol, a.info, a.trace = _fp(u), _fp(xe), info.ctypes.data_as(C.POINTER(_abi.Info)), None
+        self._check(self.lib.sdempc_fetch(self._h, C.byref(a)))
+
     def sync(self):
         self._check(self.lib.sdempc_sync(self._h))
 

@@ -31,7 +31,7 @@ def test_struct_sizes_match_header():
 
 def test_library_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "sdempc.h")).read()
-    declared = sorted(set(re.findall(r"\b(sdempc_[a-z_]+)\s*\(", hdr)))
+    declared = sorted(set(re.findall(r"\b(sdempc_[a-z0-9_]+)\s*\(", hdr)))
     assert declared == sorted(_abi.HEADER_SYMBOLS)
     lib = _abi.load_library()
     for s in declared:

@@ -70,6 +70,42 @@ def test_gloo_two_rank_gather_to_rank0(tmp_path):
     assert "GATHER0_OK" in out.stdout
 
 
+def test_gloo_two_rank_shared_memory_results(tmp_path):
+    """sharding.SharedResults (the default final gather of solve_sharded): every rank writes its slice of a shared-memory
+    array, rank 0 reads the concatenation; two generations alternate."""
+    script = tmp_path / "s.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch.distributed as dist
+        from sde4mbrl_px4_b200 import sharding
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        sr = sharding.SharedResults({{"u": (5, 3), "info": (5, 8)}})
+        prev = None
+        for rep in range(3):
+            a = sr.next()
+            a["u"][r] = 10 * r + rep
+            a["info"][r] = r - rep
+            dist.barrier()
+            if r == 0:
+                assert all(np.all(a["u"][q] == 10 * q + rep) and np.all(a["info"][q] == q - rep) for q in range(w))
+                if prev is not None:      # the previous generation is still intact
+                    assert all(np.all(prev["u"][q] == 10 * q + rep - 1) for q in range(w))
+                prev = a
+            dist.barrier()
+        if r == 0:
+            print("SHM_OK")
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29535", str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "SHM_OK" in out.stdout
+
+
 def test_gloo_two_rank_closed_loop_sharding(tmp_path):
     """BASELINE config 5 host logic at world size 2: contiguous blocks of rollouts per rank, one launch per rank,
     statistics gathered in rollout order on rank 0, device time = max over ranks.  The solver is a stand-in that

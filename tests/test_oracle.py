@@ -301,3 +301,76 @@ def test_teacher_forced_mode_replays_a_decision_trace():
     # fewer forced iterations than max_iter: stops there
     short = o32.solve_forced(pr["x"], u0, i0, a[3], np.full(B, 7.0), **kw)
     assert np.all(short[2][:, 2] == 7) and np.array_equal(short[3][:, :7], a[3][:, :7])
+
+
+def test_adaptive_momentum_and_unenforced_bounds_spec():
+    """apg_mpc.moment_scale (yaml:63-66) and enforce_ubound: False (yaml:14), [SPEC] in include/sdempc.h: with mu in (0, 1]
+    the momentum is beta_init / mu^(k-1) capped at 1 (mu = 1: constant beta_init); null keeps k / (k + 3).  The decision
+    trace of the oracle is checked against the independent float64 APG of test_independent_apg with the same rule."""
+    import os
+
+    from conftest import ROOT
+    from sde4mbrl_px4_b200 import config, model_io
+    from test_independent_apg import _torch_objective, enu2ned64
+
+    d = config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml"))
+    d["apg_mpc"].update(moment_scale=0.6, beta_init=0.2, max_iter=25, rtol=0.0, atol=0.0)
+    cfg = config.build_config(d, convert_to_enu=False, strict=True)
+    assert abs(cfg.moment_scale - 0.6) < 1e-7 and abs(cfg.beta_init - 0.2) < 1e-7
+    with pytest.raises(config.ConfigError):
+        config.build_config(dict(d, apg_mpc=dict(d["apg_mpc"], moment_scale=1.5)))
+    model = model_io.synthetic_model("iris", seed=2, weight_scale=0.3, bias_scale=0.1)
+    o = O.Oracle(cfg, model.to_blob(), "f64")
+    pr = synthetic.batched_problems(1, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=8)
+    plan = np.full((1, cfg.horizon, cfg.nu), 0.71)
+    xi = np.random.default_rng(4).standard_normal((1, 1, cfg.horizon, 6))
+    _, i0 = o.reset(1)
+    uo, _, info, tr = o.solve(pr["x"], plan, i0, xref_win=pr["xref_win"], xi=xi, want_trace=True)
+    # momentum visible in the trace: after an accepted step with counter k -> k + 1, y = clip(x+ + beta_k (x+ - x_k))
+    mu, b0 = np.float64(np.float32(0.6)), np.float64(np.float32(0.2))
+    beta = lambda k: min(1.0, b0 / mu ** (k - 1)) if k < 60 else 1.0
+
+    # independent loop with the same momentum rule
+    import test_independent_apg as T
+    Jg, Jo = _torch_objective(cfg, model, pr["x"][0].astype(np.float64), plan[0, 0].copy(), pr["xref_win"][0].astype(np.float64), xi[0])
+    H, nu = cfg.horizon, cfg.nu
+    lo, hi = np.array(cfg.u_lo[:nu], np.float64)[None], np.array(cfg.u_hi[:nu], np.float64)[None]
+    proj = lambda u: np.minimum(np.maximum(u, lo), hi)
+    p = np.concatenate([plan[0, 1:], plan[0, -1:]], axis=0)
+    xk = proj(p.copy()); yk = xk.copy()
+    s, k, Jx, rows = np.float64(i0[0, 1]), 1, None, []
+    for it in range(1, cfg.max_iter + 1):
+        fy, g = Jg(yk)
+        Jx = fy if it == 1 else Jx
+        s = min(s * np.float64(cfg.increase_factor), np.float64(cfg.max_stepsize))
+        ok = False
+        for j in range(cfg.maxls + 1):
+            xp = proj(yk - s * g); Jp = Jo(xp)
+            if Jp <= fy + np.float64(cfg.coef) * float(np.sum(g * (xp - yk))):
+                ok = True; break
+            if j < cfg.maxls:
+                s = s * np.float64(cfg.decrease_factor)
+        if ok and Jp <= Jx:
+            yk = proj(xp + beta(k) * (xp - xk)); xk = xp; Jx = Jp; k += 1
+        else:
+            yk = xk.copy(); k = 1
+        rows.append([fy, Jp, s, j + 1, float(ok and Jp <= Jx + 0), Jx, 0, k])
+    ti = np.array(rows)
+    n_it = int(info[0, 2])
+    assert n_it == cfg.max_iter and np.array_equal(tr[0, :, 3], ti[:, 3]) and np.array_equal(tr[0, :, 7], ti[:, 7])
+    assert np.abs(tr[0, :, 0] - ti[:, 0]).max() <= 1e-9 * np.abs(ti[:, 0]).max() and np.abs(uo[0] - xk).max() <= 1e-10
+    assert tr[0, :, 7].max() >= 4, "several consecutive accepted steps: the momentum actually grew"
+    # it differs from the classical rule
+    d2 = dict(d, apg_mpc=dict(d["apg_mpc"], moment_scale=None, beta_init=0.25))
+    o2 = O.Oracle(config.build_config(d2, convert_to_enu=False), model.to_blob(), "f64")
+    u2 = o2.solve(pr["x"], plan, i0, xref_win=pr["xref_win"], xi=xi)[0]
+    assert np.abs(u2 - uo).max() > 1e-6
+    # enforce_ubound: False -> no projection: a plan outside the box stays outside when the gradient does not pull it in
+    d3 = dict(d2, enforce_ubound=False)
+    c3 = config.build_config(d3, convert_to_enu=False, max_iter=3)
+    assert c3.u_lo[0] < -1e37 and c3.u_hi[0] > 1e37
+    o3 = O.Oracle(c3, model.to_blob(), "f64")
+    big = np.full((1, cfg.horizon, cfg.nu), 1.2)
+    u3 = o3.solve(pr["x"], big, i0, xref_win=pr["xref_win"], xi=xi)[0]
+    u3b = O.Oracle(config.build_config(d2, convert_to_enu=False, max_iter=3), model.to_blob(), "f64").solve(pr["x"], big, i0, xref_win=pr["xref_win"], xi=xi)[0]
+    assert u3.max() > 1.0 + 1e-3 and u3b.max() <= 1.0
