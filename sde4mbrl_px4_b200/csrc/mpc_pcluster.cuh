@@ -144,7 +144,7 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
         const bool accept = ok && (Jp <= Jx);
         bool converged = false;
         if (accept) {
-            const float beta = apg_momentum(P, k);
+            const float beta = apg_momentum_tab(P, k);
             for (int i = lane; i < n; i += 32) {
                 const int ii = i % NU;
                 const float xv = c.xp[i];

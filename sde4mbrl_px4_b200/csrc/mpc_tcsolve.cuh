@@ -265,7 +265,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     if (a != 2) {
                         const float sq = sh.s[oq];
                         const int kq = sh.k[oq];
-                        const float beta = apg_momentum(P, kq);
+                        const float beta = apg_momentum_tab(P, kq);
                         for (int i0 = part; i0 < n; i0 += 4 * nparts) {
                             float xkv[4], yv[4], gv[4];
 #pragma unroll

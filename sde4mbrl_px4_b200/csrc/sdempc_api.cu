@@ -668,6 +668,7 @@ struct sdempc_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     float* d_wimg = nullptr;
+    float* d_beta = nullptr;          // momentum table
     float* d_traj = nullptr;
     float2* d_mtape = nullptr;
     size_t mtape_warps = 0;
@@ -799,7 +800,6 @@ static void build_kparams(sdempc_handle* h) {
     for (int i = 0; i < SDEMPC_MAX_NU; ++i) { k.slew_lo[i] = c.u_slew_lo[i]; k.slew_hi[i] = c.u_slew_hi[i]; }
     k.init_step = c.init_stepsize; k.max_step = c.max_stepsize; k.coef = c.coef; k.dec_f = c.decrease_factor;
     k.inc_f = c.increase_factor; k.atol = c.atol; k.rtol = c.rtol;
-    k.moment_scale = c.moment_scale; k.beta_init = c.beta_init;
     // derived model constants: one IEEE float operation each (the oracle derives them identically)
     k.inv_m = 1.0f / m.mass; k.grav = m.gravity; k.kT = m.k_thrust; k.kT2 = 2.0f * m.k_thrust;
     for (int i = 0; i < 3; ++i) { k.J[i] = m.inertia[i]; k.Jinv[i] = 1.0f / m.inertia[i]; }
@@ -875,6 +875,21 @@ static int ensure_device(sdempc_handle* h) {
     CUDA_TRY(cudaEventCreate(&h->ev1));
     CUDA_TRY(cudaMalloc(&h->d_wimg, h->wimg.size() * 4));
     CUDA_TRY(cudaMemcpy(h->d_wimg, h->wimg.data(), h->wimg.size() * 4, cudaMemcpyHostToDevice));
+    {   // momentum table with the oracle's float operations, one entry per value of the counter k
+        std::vector<float> tab((size_t)h->cfg.max_iter + 2, 0.f);
+        for (int k = 1; k < (int)tab.size(); ++k) {
+            if (h->cfg.moment_scale == 0.f) tab[k] = (float)k / (float)(k + 3);
+            else {
+                float b = h->cfg.beta_init;
+                for (int i = 1; i < k && b < 1.0f; ++i) { b = b / h->cfg.moment_scale; b = b > 1.0f ? 1.0f : b; }
+                tab[k] = b;
+            }
+        }
+        CUDA_TRY(cudaMalloc(&h->d_beta, tab.size() * 4));
+        CUDA_TRY(cudaMemcpy(h->d_beta, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+        h->kp.beta_tab = h->d_beta; h->kp_group.beta_tab = h->d_beta;
+        h->kp.beta_adaptive = h->kp_group.beta_adaptive = (h->cfg.moment_scale != 0.f) ? 1 : 0;
+    }
     if (!h->traj_int.empty()) {
         CUDA_TRY(cudaMalloc(&h->d_traj, h->traj_int.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_traj, h->traj_int.data(), h->traj_int.size() * 4, cudaMemcpyHostToDevice));
@@ -1195,7 +1210,7 @@ void sdempc_destroy(sdempc_t* h) {
     if (h->dev_ready) {
         cudaSetDevice(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
-        cudaFree(h->d_wimg); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_mtape_group); cudaFree(h->d_in); cudaFree(h->d_out);
+        cudaFree(h->d_wimg); cudaFree(h->d_beta); cudaFree(h->d_traj); cudaFree(h->d_mtape); cudaFree(h->d_mtape_group); cudaFree(h->d_in); cudaFree(h->d_out);
         cudaFree(h->d_trace); cudaFree(h->d_flush); cudaFree(h->d_wimg_tc); cudaFree(h->d_tape_tc); cudaFree(h->d_tcs_ws);
         if (h->h_in) cudaFreeHost(h->h_in);
         if (h->h_out) cudaFreeHost(h->h_out);

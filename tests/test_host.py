@@ -247,3 +247,46 @@ def test_horizon_bound_and_beta_init_are_checked():
         config.build_config(db)
     with pytest.raises(config.ConfigError, match="beta_init"):
         config.build_config(db, strict=True)
+
+
+def test_haiku_param_converter_on_a_fabricated_flat_npz(tmp_path):
+    """tools/convert_haiku_params.py: a flat .npz with Haiku-style keys and [in, out] Linear weights is mapped
+    onto this framework's model format; the converted model loads, packs into a blob sdempc_create accepts, and carries
+    exactly the fabricated tensors (transposed); a wrong shape or a missing key is rejected with a message."""
+    import json
+    import subprocess
+    import sys
+
+    from sde4mbrl_px4_b200 import solver
+
+    rng = np.random.default_rng(0)
+    nu, W = 4, 32
+    shapes = {"W1": (6 + nu, W), "b1": (W,), "W2": (W, W), "b2": (W,), "W3": (W, 6), "b3": (6,)}   # Haiku: [in, out]
+    flat, mp = {}, {"transpose": True, "mass": 1.3, "k_thrust": 7.5, "inertia": [0.03, 0.03, 0.06], "sigma_prior": [0.1] * 6}
+    for net, mod in (("drift", "sde_rotor_model/~/residual_forces"), ("diff", "sde_rotor_model/~/diffusion_scaler")):
+        for i, lay in enumerate(("W1", "b1", "W2", "b2", "W3", "b3")):
+            key = f"{mod}/linear_{i // 2}/{'w' if lay[0] == 'W' else 'b'}"
+            flat[key] = rng.standard_normal(shapes[lay]).astype(np.float32)
+            mp[f"{net}_{lay}"] = key
+    fpath, mpath, out = tmp_path / "flat.npz", tmp_path / "map.json", tmp_path / "model.npz"
+    np.savez(fpath, **flat)
+    json.dump(mp, open(mpath, "w"))
+    tool = os.path.join(ROOT, "tools", "convert_haiku_params.py")
+    r = subprocess.run([sys.executable, tool, str(fpath), str(out), "--vehicle", "iris", "--map", str(mpath)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-1500:]
+    m = model_io.SDEModel.load(str(out))
+    assert (m.nu, m.width) == (nu, W) and abs(m.mass - 1.3) < 1e-6 and abs(m.k_thrust - 7.5) < 1e-6
+    assert np.array_equal(m.weights["drift_W1"], flat[mp["drift_W1"]].T) and np.array_equal(m.weights["diff_b3"], flat[mp["diff_b3"]])
+    cfg = config.build_config(config.load_yaml(os.path.join(ROOT, "configs", "iris_traj.yaml")))
+    solver.MPCSolver(cfg, m.to_blob()).close()          # the blob is what sdempc_create takes (host only)
+    # a layer of the wrong shape is rejected, not silently reshaped
+    bad = dict(flat)
+    bad[mp["drift_W2"]] = rng.standard_normal((W, W + 1)).astype(np.float32)
+    np.savez(fpath, **bad)
+    r = subprocess.run([sys.executable, tool, str(fpath), str(out), "--vehicle", "iris", "--map", str(mpath)], capture_output=True, text=True)
+    assert r.returncode != 0 and "does not fit" in (r.stderr + r.stdout)
+    mp2 = dict(mp, diff_W3="no/such/key")
+    json.dump(mp2, open(mpath, "w"))
+    np.savez(fpath, **flat)
+    r = subprocess.run([sys.executable, tool, str(fpath), str(out), "--vehicle", "iris", "--map", str(mpath)], capture_output=True, text=True)
+    assert r.returncode != 0 and "not found" in (r.stderr + r.stdout)

@@ -12,6 +12,7 @@ import sys
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 flt = sys.argv[3] if len(sys.argv) > 3 else ""
+by_inst = len(sys.argv) > 4 and sys.argv[4] == "inst"   # sort by executed warp-instructions instead of stall samples
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 out, fname, h, ix, scols = [], "", None, None, None
@@ -39,6 +40,7 @@ byfile = collections.Counter()
 for t, ex, f, ln, text, st in out:
     byfile[f] += t
 print("# by file: " + ", ".join(f"{f} {100.0 * v / total:.1f}%" for f, v in byfile.most_common(6)))
-for t, ex, f, ln, text, st in sorted([o for o in out if flt in o[2]], key=lambda r: -r[0])[:top]:
+tot_inst = sum(r[1] for r in out) or 1
+for t, ex, f, ln, text, st in sorted([o for o in out if flt in o[2]], key=lambda r: -(r[1] if by_inst else r[0]))[:top]:
     reasons = ", ".join(f"{k.replace('stall_', '')} {100.0 * v / max(t, 1):.0f}%" for k, v in collections.Counter(st).most_common(3) if v)
-    print(f"{100.0 * t / total:6.2f} %  inst {ex:9d}  {f}:{ln:>4s}  [{reasons}]  {text.strip()[:100]}")
+    print(f"{100.0 * t / total:6.2f} %  inst {100.0 * ex / tot_inst:5.2f} %  {f}:{ln:>4s}  [{reasons}]  {text.strip()[:100]}")
