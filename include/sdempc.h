@@ -59,10 +59,12 @@ extern "C" {
 #define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
 #define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
 #define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a 2-CTA cluster */
-#define SDEMPC_F_TENSOR 64u        /* sdempc_rollout (value_and_grad; 1, 2, 4 ... 32 particles): network layers and their adjoints on the tensor \
-                                      cores (tcgen05, TF32 operands, fp32 accumulation, tanh.approx); NOT bit-identical to the \
-                                      FP32 path: costs, trajectories and gradients agree within the tolerance stated in \
-                                      DESIGN.md section 5 */
+#define SDEMPC_F_TENSOR 64u        /* batched sdempc_solve_ex / sdempc_solve (m_mpc) and sdempc_rollout (value_and_grad) with 1, 2, 4 ... 32       \
+                                      particles: network layers and their adjoints on the tensor cores (tcgen05, TF32 operands, fp32         \
+                                      accumulation, tanh.approx), the whole APG loop on that mapping (mpc_tcsolve.cuh).  NOT bit-identical   \
+                                      to the FP32 path: compared with the oracle teacher-forced and at cost level within the bound stated    \
+                                      in DESIGN.md section 5.2.  Refuses the soft input-rate constraint.  Pays off from a few thousand        \
+                                      rollout rows (problems x particles) per launch; a single tick stays on the FP32 kernels. */
 /* Default kernel choice: latency kernels when the batch fits one problem per SM (or per cluster), the throughput
  * kernel for large batches (> ~13 problems per SM; P = 1, width 32), one warp per (problem, particle) otherwise.
  * All of them produce bit-identical results. */
