@@ -957,14 +957,20 @@ static bool use_group(const sdempc_handle* h, int B) {
     return B > per_sm * h->sm_count;
 }
 
-// Tensor-core solve (SDEMPC_F_TENSOR): problems per CTA.  A CTA has 128 / P rollout slots and is latency bound when it
-// is alone on its SM (measured, 4096 iris problems x 200 iterations: 28 problems per CTA on 147 SMs 41 ms; 25 per CTA =
-// the whole line search in one pass but 164 CTAs on 148 SMs 47 ms; 14 per CTA, two CTAs per SM, 45 ms; 7 per CTA 63 ms):
-// spread the batch over the SMs first, one CTA each, and only share an SM between CTAs when the slots are full.
+// Tensor-core solve (SDEMPC_F_TENSOR): problems per CTA.  A CTA has NT = 128 / P rollout slots.  Measured (iris, 200
+// iterations): a CTA alone on its SM is latency bound (2.5 us per step evaluation), two CTAs on an SM slow each other
+// 1.4x, four 1.8x; NT / 4 problems per CTA need two line-search passes per iteration (80 step evaluations), NT problems
+// about three plus a full-width gradient pass (100).  4096 problems: 28 per CTA on 147 SMs 40.0 ms, 14 per CTA (two CTAs
+// per SM, one line-search pass) 42.7 ms, 7 per CTA 53.3 ms; 16 384 problems: 32 per CTA (512 CTAs) 56.4 ms, 64 per CTA
+// 61.2 ms, 128 per CTA 74.5 ms.  So: one CTA per SM with up to NT / 4 problems, then more CTAs per SM at NT / 4 problems
+// until the SMs are full (512 / columns resident CTAs), and only then more problems per CTA.
 static int tcs_problems_per_cta(const sdempc_handle* h, int B) {
     const int P = h->cfg.num_particles, NT = 128 / P;
     if (h->tcs_ppc_override > 0) return std::min(h->tcs_ppc_override, NT);
-    const int ppc = (B + h->sm_count - 1) / h->sm_count;
+    const int base = std::max(1, NT / 4);
+    const int resident = h->sm_count * (512 / std::max(1, h->kc.tc_cols));
+    int ppc = (B + h->sm_count - 1) / h->sm_count;                 // one CTA per SM
+    if (ppc > base) ppc = std::max(base, (B + resident - 1) / resident);   // fill the SMs at NT / 4 problems per CTA, then grow
     return std::max(1, std::min(ppc, NT));
 }
 
