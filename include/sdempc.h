@@ -229,6 +229,11 @@ int sdempc_device_out(sdempc_t* h, void** dev_ptr, size_t* nbytes);
 /* D2H of the outputs of the last launch into `args` and stream synchronise. */
 int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args);
 
+/* sdempc_fetch without the staging copy: device -> host straight into args->x_evol / u_plan / info.  Meant for page-locked
+ * destinations (cudaHostRegister'ed, e.g. every rank's slice of a shared-memory result array in the multi-GPU gather);
+ * pageable destinations work but are slower than sdempc_fetch. */
+int sdempc_fetch_direct(sdempc_t* h, const sdempc_solve_args* args);
+
 /* CUDA-event duration (ms) of the most recent kernel launch of this handle, on its own stream. */
 float sdempc_last_launch_ms(const sdempc_t* h);
 /* Kernels launched by this handle so far (for bench.py's gpu_launches). */

@@ -1155,11 +1155,19 @@ static void (*staged_kernel(const sdempc_handle* h))(KParams) {
            : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
-static int fetch_solve(sdempc_handle* h, const sdempc_solve_args* a) {
+static int fetch_solve(sdempc_handle* h, const sdempc_solve_args* a, bool direct = false) {
     if (!h->staged_ok || a->B != h->staged_B) return fail(SDEMPC_ESTATE, "fetch without a matching stage");
     const int B = a->B, H = h->cfg.horizon, NU = h->cfg.nu, n = H * NU;
     const size_t o_x = 0, o_p = a16((size_t)B * (H + 1) * NX * 4), o_i = o_p + a16((size_t)B * n * 4);
     const size_t total = o_i + a16((size_t)B * sizeof(sdempc_info));
+    if (direct) {   // the caller's buffers are page-locked (cudaHostRegister): copy straight into them, no staging copy
+        CUDA_TRY(cudaMemcpyAsync(a->x_evol, h->d_out + o_x, (size_t)B * (H + 1) * NX * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(a->u_plan, h->d_out + o_p, (size_t)B * n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(a->info, h->d_out + o_i, (size_t)B * sizeof(sdempc_info), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        for (int b = 0; b < B; ++b) a->info[b].solve_time_us = h->last_ms * 1000.f;
+        return 0;
+    }
     CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     memcpy(a->x_evol, h->h_out + o_x, (size_t)B * (H + 1) * NX * 4);
@@ -1354,6 +1362,13 @@ int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args) {
     if (!h || !args) return fail(SDEMPC_EINVAL, "null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     return fetch_solve(h, args);
+}
+
+int sdempc_fetch_direct(sdempc_t* h, const sdempc_solve_args* args) {
+    if (!h || !args) return fail(SDEMPC_EINVAL, "null argument");
+    if (!args->x_evol || !args->u_plan || !args->info) return fail(SDEMPC_EINVAL, "x_evol, u_plan and info are required");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return fetch_solve(h, args, true);
 }
 
 int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {

@@ -299,6 +299,27 @@ class SDEControlNode:
         self.dt_state_callback = time.time() - t_in
         return cmd
 
+    # ------------------------------------------------------------------ MAVLink edge (:142-154, 605-613)
+    def feed_mavlink(self, data: bytes) -> bytes:
+        """Byte-level edge of the node: ``data`` is what mavlink-router delivers (scripts/router_sitl.conf:18-19).  Every
+        complete MPC_FULL_STATE frame (id 367) goes through ``mpc_state_callback`` — the body of the reference's
+        ``read_mavlink_msg`` loop (:142-154) — and every resulting command is returned as an MPC_MOTORS_CMD frame (id 368),
+        what ``pub_cmd_setpoint`` (:605-613) sends.  Other message ids and corrupted frames are skipped."""
+        from . import mavlink_codec as mv
+
+        if getattr(self, "_mav_decoder", None) is None:
+            self._mav_decoder, self._mav_seq = mv.Decoder(), 0
+        out = b""
+        for msg, values, _ in self._mav_decoder.feed(data):
+            if msg.msgid != mv.MPC_FULL_STATE.msgid:
+                continue
+            cmd = self.mpc_state_callback(values)
+            if cmd is not None:
+                out += mv.encode(mv.MPC_MOTORS_CMD, mv.motors_cmd_values(cmd["time_usec"], cmd["motor_val_des"], cmd["thrust_and_angrate_des"],
+                                                                        cmd["mpc_on"], cmd["weight_motors"]), seq=self._mav_seq)
+                self._mav_seq = (self._mav_seq + 1) & 0xFF
+        return out
+
     # ------------------------------------------------------------------ services (:453-562)
     def initialize_mpc(self) -> bool:
         """``controller_init`` -> set_trajectory_and_params (:453-477): refused while a controller runs;

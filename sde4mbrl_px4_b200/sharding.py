@@ -137,6 +137,20 @@ class SharedResults:
                 segs = [shared_memory.SharedMemory(name=nm) for nm in names]
             self._segs.append(segs)
             self.arrays.append({k: np.ndarray((self.world,) + tuple(sh), np.float32, buffer=sg.buf) for (k, sh), sg in zip(shapes.items(), segs)})
+        # page-lock this rank's own slices so that the device-to-host copy goes straight into them (sdempc_fetch_direct)
+        self.registered = False
+        try:
+            import torch
+            if torch.cuda.is_available():
+                rt = torch.cuda.cudart()
+                ok = True
+                for arrs in self.arrays:
+                    for a in arrs.values():
+                        sl = a[self.rank]
+                        ok = ok and int(rt.cudaHostRegister(sl.ctypes.data, sl.nbytes, 0)) == 0
+                self.registered = ok
+        except Exception:
+            self.registered = False
         dist.barrier()
         if self.rank == 0:       # the mappings stay valid; the names disappear at once so nothing leaks if a rank dies
             for segs in self._segs:
@@ -179,7 +193,7 @@ def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int, gather: 
             _gather_cache["shared"] = SharedResults({k: shape for k, (off, shape) in layout.items()})
     if gather == "shm":
         arrs = _gather_cache["shared"].next()
-        solver.fetch_into(arrs["u"][rank], arrs["x_evol"][rank], arrs["info"][rank])
+        solver.fetch_into(arrs["u"][rank], arrs["x_evol"][rank], arrs["info"][rank], direct=_gather_cache["shared"].registered)
         dist.barrier()
         if rank != 0:
             return None

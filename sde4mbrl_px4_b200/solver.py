@@ -154,9 +154,10 @@ class MPCSolver:
         self._check(self.lib.sdempc_fetch(self._h, C.byref(a)))
         return keep["u"], keep["xe"], keep["info"]
 
-    def fetch_into(self, u, xe, info):
-        """D2H of the staged solve's outputs straight into caller-provided float32 arrays (e.g. slices of a shared-memory
-        result buffer): u[B,H,nu], xe[B,H+1,13], info[B,8]."""
+    def fetch_into(self, u, xe, info, direct: bool = False):
+        """D2H of the staged solve's outputs into caller-provided float32 arrays (e.g. slices of a shared-memory result
+        buffer): u[B,H,nu], xe[B,H+1,13], info[B,8].  ``direct=True`` skips the pinned staging copy (`sdempc_fetch_direct`):
+        for destinations the caller has page-locked with cudaHostRegister."""
         a0, keep = self._staged
         B = keep["x"].shape[0]
         for arr, shape in ((u, (B, self.H, self.nu)), (xe, (B, self.H + 1, 13)), (info, (B, 8))):
@@ -165,7 +166,7 @@ class MPCSolver:
         a = _abi.SolveArgs()
         C.memmove(C.byref(a), C.byref(a0), C.sizeof(a))
         a.u_plan, a.x_evol, a.info, a.trace = _fp(u), _fp(xe), info.ctypes.data_as(C.POINTER(_abi.Info)), None
-        self._check(self.lib.sdempc_fetch(self._h, C.byref(a)))
+        self._check((self.lib.sdempc_fetch_direct if direct else self.lib.sdempc_fetch)(self._h, C.byref(a)))
 
     def sync(self):
         self._check(self.lib.sdempc_sync(self._h))

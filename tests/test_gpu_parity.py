@@ -434,7 +434,9 @@ def test_tensor_core_solve_modes_and_batches(solver, O):
             assert np.median(np.abs(up - upo).reshape(B, -1).max(axis=1)) <= 1e-4
             assert np.abs(xe - xeo)[:nchk].max() <= 2e-2
         ki = s.kernel_info()
-        assert ki["problems_per_cta"] == min(128, -(-B // ki["sm_count"])) and ki["ctas"] == -(-B // ki["problems_per_cta"]), (B, ki)
+        ppc = -(-B // ki["sm_count"])                 # one CTA per SM up to 32 problems, then fill the SMs (4 CTAs each), then grow
+        ppc = ppc if ppc <= 32 else min(128, max(32, -(-B // (4 * ki["sm_count"]))))
+        assert ki["problems_per_cta"] == ppc and ki["ctas"] == -(-B // ppc), (B, ki)
     # set-point mode and early stopping with the YAML tolerances
     cfgp, blobp, _ = make_setup("iris", "traj", tensor=True)   # set-point mode: xdes instead of a trajectory time
     sp, op = solver.MPCSolver(cfgp, blobp), O.Oracle(make_setup("iris", "traj")[0], blobp, "f32")

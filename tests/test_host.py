@@ -290,3 +290,63 @@ def test_haiku_param_converter_on_a_fabricated_flat_npz(tmp_path):
     np.savez(fpath, **flat)
     r = subprocess.run([sys.executable, tool, str(fpath), str(out), "--vehicle", "iris", "--map", str(mpath)], capture_output=True, text=True)
     assert r.returncode != 0 and "not found" in (r.stderr + r.stdout)
+
+
+def test_mavlink_codec_public_known_answers_and_round_trip():
+    """sde4mbrl_px4_b200/mavlink_codec.py: the MAVLink 2 framing is checked against PUBLIC known answers
+    (CRC-16/MCRF4XX check value; CRC_EXTRA of HEARTBEAT / ATTITUDE / LOCAL_POSITION_NED from the common dialect), then the
+    two messages of the reference's edge (ids 367 / 368, scripts/router_sitl.conf:18-19) round-trip, including zero
+    truncation, wire reordering, resynchronisation after garbage and rejection of a corrupted frame."""
+    from sde4mbrl_px4_b200 import mavlink_codec as mv
+
+    assert mv.x25_crc(b"123456789") == 0x6F91
+    F = mv.Field
+    hb = mv.MessageDef("HEARTBEAT", 0, (F("type", "uint8_t"), F("autopilot", "uint8_t"), F("base_mode", "uint8_t"), F("custom_mode", "uint32_t"),
+                                        F("system_status", "uint8_t"), F("mavlink_version", "uint8_t")))
+    att = mv.MessageDef("ATTITUDE", 30, (F("time_boot_ms", "uint32_t"),) + tuple(F(n, "float") for n in ("roll", "pitch", "yaw", "rollspeed", "pitchspeed", "yawspeed")))
+    lpn = mv.MessageDef("LOCAL_POSITION_NED", 32, (F("time_boot_ms", "uint32_t"),) + tuple(F(n, "float") for n in ("x", "y", "z", "vx", "vy", "vz")))
+    assert (hb.crc_extra, att.crc_extra, lpn.crc_extra) == (50, 39, 185)
+    assert [f.name for f in hb.wire_fields][0] == "custom_mode"          # largest element first, stable otherwise
+    assert (mv.MPC_FULL_STATE.msgid, mv.MPC_MOTORS_CMD.msgid) == (367, 368)
+    # a HEARTBEAT frame byte for byte as a MAVLink 2 GCS emits it (type 6 GCS, autopilot 8 invalid, seq 0, sys 255, comp 190)
+    fr = mv.encode(hb, dict(type=6, autopilot=8, base_mode=0, custom_mode=0, system_status=0, mavlink_version=3), seq=0, sysid=255, compid=190)
+    assert fr[:10] == bytes([0xFD, 9, 0, 0, 0, 255, 190, 0, 0, 0]) and fr[10:19] == bytes([0, 0, 0, 0, 6, 8, 0, 0, 3])
+    # state message: values survive, trailing zeros (m1..m4 = 0, wz = 0) are truncated from the payload
+    st = dict(time_usec=1_234_567, x=1.5, y=-2.0, z=3.25, vx=0.1, vy=0.2, vz=0.3, qw=1.0, qx=0.0, qy=0.0, qz=0.0, wx=0.5, wy=-0.5, wz=0.0,
+              m1=0, m2=0, m3=0, m4=0)
+    f1 = mv.encode(mv.MPC_FULL_STATE, st, seq=7)
+    assert f1[1] == 8 + 12 * 4 and f1[1] < mv.MPC_FULL_STATE.payload_size
+    cmd = mv.motors_cmd_values(99, [0.1, 0.2, 0.3, 0.4], [0.25, 1, 2, 3], 3, 255.0)
+    f2 = mv.encode(mv.MPC_MOTORS_CMD, cmd, seq=8)
+    dec = mv.Decoder()
+    unknown = bytes([0xFD, 1, 0, 0, 0, 1, 1, 0x10, 0x27, 0, 5, 0, 0])          # id 10000: skipped
+    got = dec.feed(b"\x00\x11garbage" + f1[:20]) + dec.feed(f1[20:] + unknown + f2)
+    assert [g[0].name for g in got] == ["MPC_FULL_STATE", "MPC_MOTORS_CMD"] and dec.skipped == 1 and got[0][2]["seq"] == 7
+    x, t = mv.state_from_full_state(got[0][1])
+    assert t == 1_234_567 and np.allclose(x, [1.5, -2.0, 3.25, 0.1, 0.2, 0.3, 1, 0, 0, 0, 0.5, -0.5, 0.0])
+    assert np.allclose(got[1][1]["motor_val_des"], [0.1, 0.2, 0.3, 0.4, 0, 0]) and got[1][1]["mpc_on"] == 3 and got[1][1]["weight_motors"] == 255.0
+    bad = bytearray(f1)
+    bad[15] ^= 0x40
+    assert mv.Decoder().feed(bytes(bad)) == [] and len(mv.Decoder().feed(bytes(bad) + f2)) == 1
+
+
+def test_node_byte_level_mavlink_edge():
+    """MPC_FULL_STATE frames in, MPC_MOTORS_CMD frames out (read_mavlink_msg + pub_cmd_setpoint, sde_control.py:142-154, 605-613)."""
+    from sde4mbrl_px4_b200 import mavlink_codec as mv
+
+    n = node.SDEControlNode("cfg", "traj.yaml", "pos.yaml", seed=10, use_process=False, loader=_stub_loader, clock=lambda: 100.0)
+    try:
+        frame = lambda t: mv.encode(mv.MPC_FULL_STATE, dict(_msg(t), m1=0.5, m2=0.5, m3=0.5, m4=0.5))
+        assert n.feed_mavlink(frame(1_000_000)) == b""                    # state 'none': nothing is sent
+        assert n.initialize_mpc() and n.start_trajectory(node.CTRL_TEST, target_pose=(1, 2, 3, 1, 0, 0, 0))
+        out = n.feed_mavlink(frame(1_050_000)[:30])
+        assert out == b""                                                 # incomplete frame: buffered
+        out = n.feed_mavlink(frame(1_050_000)[30:] + frame(1_100_000))
+        cmds = mv.Decoder().feed(out)
+        assert len(cmds) == 2 and all(c[0].msgid == 368 for c in cmds) and [c[2]["seq"] for c in cmds] == [0, 1]
+        v = cmds[0][1]
+        assert v["mpc_on"] == node.CONTROL_STATES["test"] and v["time_usec"] == 100_000_000
+        assert np.allclose(v["motor_val_des"][:4], 0.002 * np.arange(1, 5)) and np.allclose(v["motor_val_des"][4:], 0)
+        assert np.allclose(v["thrust_and_angrate_des"], [0.002 * 2.5, 1.0, 2.0, 3.0])
+    finally:
+        n.close()
