@@ -135,6 +135,12 @@ class SharedResults:
             dist.broadcast_object_list(names, src=0)
             if self.rank != 0:
                 segs = [shared_memory.SharedMemory(name=nm) for nm in names]
+                try:     # attaching registers the segment with this process's resource tracker too (Python < 3.13); rank 0 owns it
+                    from multiprocessing import resource_tracker
+                    for sg in segs:
+                        resource_tracker.unregister(sg._name, "shared_memory")
+                except Exception:
+                    pass
             self._segs.append(segs)
             self.arrays.append({k: np.ndarray((self.world,) + tuple(sh), np.float32, buffer=sg.buf) for (k, sh), sg in zip(shapes.items(), segs)})
         # page-lock this rank's own slices so that the device-to-host copy goes straight into them (sdempc_fetch_direct)

@@ -592,6 +592,45 @@ def test_full_size_batch_4096(solver, O):
     _eq(a[0], u[:64], "staged relaunch"); assert np.all(ms > 0)
 
 
+@pytest.mark.parametrize("vehicle,particles,B", [("iris", 1, 65536), ("hexa", 8, 8192)])
+def test_tensor_core_solve_full_size(solver, O, vehicle, particles, B):
+    """The tensor-core solve at the sizes bench.py reports (65 536 rollout rows, 200 iterations): size-independent
+    properties on every problem (finite, inside the box, monotone descent, opt_cost = the FP32 rollout cost of the returned
+    plan, staged relaunch idempotent, independence of batch composition up to the stated bound) and the oracle at cost
+    level on a random subset."""
+    cfg_t, blob, _ = make_setup(vehicle, "traj", tensor=True, num_particles=particles, rtol=0.0, atol=0.0)
+    cfg_f, _, _ = make_setup(vehicle, "traj", num_particles=particles, rtol=0.0, atol=0.0)
+    s, sf, o = solver.MPCSolver(cfg_t, blob), solver.MPCSolver(cfg_f, blob), O.Oracle(cfg_f, blob, "f32")
+    H = cfg_f.horizon
+    pr = synthetic.batched_problems(B, H, np.array(cfg_f.dt[:H]), seed=0)
+    u0, i0 = s.reset(B)
+    s.stage(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"])
+    s.launch_timed(1, flush_l2=False)
+    u, xe, info = [a.copy() for a in s.fetch()]
+    lo, hi = np.array(cfg_f.u_lo[: cfg_f.nu], np.float32), np.array(cfg_f.u_hi[: cfg_f.nu], np.float32)
+    assert np.all(np.isfinite(u)) and np.all(np.isfinite(xe)) and np.all(np.isfinite(info[:, :7]))
+    assert np.all(u >= lo) and np.all(u <= hi)
+    # rtol = atol = 0 still stops a solve whose accepted step leaves the cost bit-for-bit unchanged ([SPEC] step 6): rare
+    assert np.all(info[:, 2] <= cfg_f.max_iter) and info[:, 2].mean() >= cfg_f.max_iter - 1
+    assert np.all(info[:, 6] <= info[:, 5]) and np.median(info[:, 6] / info[:, 5]) < 0.5
+    assert np.all(info[:, 0] >= 1) and np.all(info[:, 0] <= cfg_f.maxls + 1) and 1.5 < info[:, 0].mean() < 2.3
+    assert np.array_equal(xe[:, 0], pr["x"])
+    s.launch_timed(1, flush_l2=True)                       # staged relaunch on the same inputs: identical results
+    u2, xe2, info2 = s.fetch()
+    _eq(u2, u, "staged relaunch"); _eq(info2[:, :7], info[:, :7], "staged relaunch telemetry")
+    idx = np.random.default_rng(1).choice(B, 96, replace=False)
+    # opt_cost is J(u*): re-evaluated by the FP32 (bit-exact) rollout kernel within the tensor-core rollout bound
+    J, _, xef = sf.rollout(pr["x"][idx], u[idx], u0[idx, 0], xref_win=pr["xref_win"][idx], rng=pr["rng"][idx], want_grad=False)
+    assert np.max(np.abs(J - info[idx, 6]) / np.abs(J)) <= 1e-4 and np.abs(xef - xe[idx]).max() <= 1e-3
+    # the oracle, free running, on the subset: cost level (a subset solved alone lands in other CTAs / slots: same bound)
+    uo, _, io, _ = o.solve(pr["x"][idx], u0[idx], i0[idx], xref_win=pr["xref_win"][idx], rng=pr["rng"][idx])
+    rc = np.abs(info[idx, 6] - io[:, 6]) / np.abs(io[:, 6])
+    assert np.median(rc) <= 1e-4 and np.quantile(rc, 0.9) <= 2e-2 and rc.max() <= 5e-2, (np.median(rc), rc.max())
+    us, _, infos, _ = s.solve(pr["x"][idx], u0[idx], i0[idx], xref_win=pr["xref_win"][idx], rng=pr["rng"][idx])
+    rs = np.abs(infos[:, 6] - info[idx, 6]) / np.abs(info[idx, 6])
+    assert np.median(rs) <= 1e-5, "batch composition changes nothing but the slot a rollout runs in"
+
+
 def test_closed_loop_monte_carlo(solver, O):
     """BASELINE config 5 in miniature: plant + MPC ticks entirely on device, identical to the oracle's loop."""
     cfg, s, o = _pair(solver, O, "iris", "traj", max_iter=15, rtol=0.0, atol=0.0)
