@@ -1,0 +1,7 @@
+// kern_d.cu — instantiation unit of the FP32 (SPEC-ARITH) kernels: (4, 64, 1) (nu, width, particles).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -c kern_d.cu
+#include "mpc_entry.cuh"
+
+namespace sdempc {
+KernelChoice choice_4_64_1() { return make_choice<4, 64, 1, 8>(); }
+}  // namespace sdempc
