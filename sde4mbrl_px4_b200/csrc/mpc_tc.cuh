@@ -134,6 +134,24 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_plain(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nTMW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TMD;\nbra TMW;\nTMD:\n}\n" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 }  // namespace tc
 
 // reference row t (internal frame) of problem b: explicit window, trajectory time or fixed set-point
@@ -156,31 +174,35 @@ __device__ __forceinline__ void tc_ref_row(const KParams& P, int b, int t, float
     }
 }
 
-// Body of the kernel (entry point in sdempc_api.cu).  wimg: TCLayout image in global memory.
+// Body of the kernel (entry point in sdempc_tc.cu).  wimg: TCLayout image in global memory.  bar: two mbarriers.
 template <int NU, int W, bool GRAD>
 __device__ __forceinline__ void tc_rollout_body(const KParams& P, unsigned char* sB, uint32_t* tmem_base_slot, uint64_t* bar) {
     using L = TCLayout<NU, W>;
     constexpr int NIN = L::NIN, N12 = L::N12;
     constexpr int IMG = GRAD ? L::BYTES_GRAD : L::BYTES;
     const int tid = threadIdx.x, warp = tid >> 5;
-    // ---- one-time setup: weights to shared memory, barrier, tensor memory ----
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(P.wimg);
-        uint4* dst = reinterpret_cast<uint4*>(sB);
-        for (int i = tid; i < IMG / 16; i += 128) dst[i] = __ldg(src + i);
-    }
+    // ---- one-time setup: weights to shared memory by a TMA bulk copy (SASS UBLKCP), barriers, tensor memory ----
+    uint64_t* wbar = bar + 1;            // bar[0]: contraction complete, bar[1]: weight image landed
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(bar)));
+        tc::mbar_init(bar, 1);
+        tc::mbar_init(wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        constexpr uint32_t CH = 32768;
+        tc::mbar_expect_tx(wbar, IMG);
+        for (uint32_t off = 0; off < (uint32_t)IMG; off += CH)
+            tc::bulk_g2s(sB + off, reinterpret_cast<const unsigned char*>(P.wimg) + off, ((uint32_t)IMG - off) < CH ? ((uint32_t)IMG - off) : CH, wbar);
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_slot)), "r"((uint32_t)L::COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic-proxy stores) -> tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc::mbar_wait_plain(wbar, 0);        // the async proxy wrote what tcgen05.mma (async proxy) and the bias loads read
     const uint32_t tb = *tmem_base_slot;
     const uint32_t lane_addr = tb + ((uint32_t)(warp * 32) << 16);
     const uint32_t sb = tc::smem_u32(sB);

@@ -80,24 +80,6 @@ __device__ __forceinline__ void softplus_sigmoid_fast(float s, float& sp, float&
     sp = fmaxf(s, 0.f) + lg2_approx(1.0f + e) * 0.6931471805599453f;
     sg = s >= 0.f ? r : e * r;
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_plain(uint64_t* bar, uint32_t parity) {
-    asm volatile("{\n.reg .pred p;\nTMW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra TMD;\nbra TMW;\nTMD:\n}\n" ::"r"(smem_u32(bar)),
-                 "r"(parity)
-                 : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 }  // namespace tc
 
 // Body of the solve kernel.  sB: weight image (TCLayout, forward + adjoint parts).  bars[0]: weight staging, bars[1]: MMA.

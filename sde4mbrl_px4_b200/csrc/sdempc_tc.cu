@@ -14,8 +14,8 @@ template <int NU, int W, bool GRAD>
 __global__ void __launch_bounds__(128, 512 / TCLayout<NU, W>::COLS) mpc_tc_rollout_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
-    __shared__ __align__(8) uint64_t tc_bar;
-    tc_rollout_body<NU, W, GRAD>(P, tc_smem, &tmem_slot, &tc_bar);
+    __shared__ __align__(8) uint64_t tc_bar[2];
+    tc_rollout_body<NU, W, GRAD>(P, tc_smem, &tmem_slot, tc_bar);
 }
 
 template <int NU, int W>
