@@ -106,7 +106,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or os.environ.get("SDEMPC_LIB") or LIB_PATH   # SDEMPC_LIB: experiment builds (tools/dev_build.sh)
+    p = path or os.environ.get("SDEMPC_LIB") or LIB_PATH   # SDEMPC_LIB: experiment builds (tools/ab_variant.sh)
     if not os.path.exists(p):
         raise RuntimeError(
             f"{p} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "

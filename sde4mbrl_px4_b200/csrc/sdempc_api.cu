@@ -68,7 +68,7 @@ KernelChoice choice_6_64_8();
 static const std::vector<KernelChoice>& choices() {
     static const std::vector<KernelChoice> v = [] {
         std::vector<KernelChoice> c = {
-#ifdef SDEMPC_DEV_IRIS_ONLY   // quick experiment builds: the bench shape only
+#ifdef SDEMPC_DEV_IRIS_ONLY   // quick experiment builds (link kern_a.o only): the bench shape only
             choice_4_32_1(),
 #else
             choice_4_32_1(), choice_4_32_2(), choice_4_32_4(), choice_4_32_8(), choice_6_32_1(), choice_6_32_8(),

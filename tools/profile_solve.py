@@ -16,7 +16,7 @@ ap.add_argument("--iters", type=int, default=200)
 ap.add_argument("--vehicle", default="iris")
 ap.add_argument("--particles", type=int, default=1)
 ap.add_argument("--launches", type=int, default=1)
-ap.add_argument("--lib", default=None, help="alternative libsdempc build (tools/dev_build.sh)")
+ap.add_argument("--lib", default=None, help="alternative libsdempc build (tools/ab_variant.sh)")
 a = ap.parse_args()
 cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{a.vehicle}_traj.yaml"))
 cfg = config.build_config(cfgd, max_iter=a.iters, rtol=0.0, atol=0.0, num_particles=a.particles)
