@@ -448,6 +448,23 @@ def test_tensor_core_solve_modes_and_batches(solver, O):
     a, b = sp.solve(x, u0, i0, xdes=xd, rng=rng), op.solve(x, u0, i0, xdes=xd, rng=rng)
     assert np.median(np.abs(a[2][:, 6] - b[2][:, 6]) / np.abs(b[2][:, 6])) <= 1e-4
     assert np.median(np.abs(a[2][:, 2] - b[2][:, 2])) <= 2, "early stopping triggers at (nearly) the same iteration"
+    # explicit noise (the test hook that would carry another generator's samples) and SDEMPC_F_NO_SHIFT
+    cfgn, blobn, _ = make_setup("iris", "traj", tensor=True, no_shift=True, max_iter=25, num_particles=2)
+    sn, on = solver.MPCSolver(cfgn, blobn), O.Oracle(make_setup("iris", "traj", no_shift=True, max_iter=25, num_particles=2)[0], blobn, "f32")
+    Bn = 21
+    prn = synthetic.batched_problems(Bn, cfgn.horizon, np.array(cfgn.dt[: cfgn.horizon]), seed=12)
+    xi = np.random.default_rng(2).standard_normal((Bn, 2, cfgn.horizon, 6)).astype(np.float32)
+    un, in_ = sn.reset(Bn)
+    un = np.clip(un + 0.05 * np.random.default_rng(3).standard_normal(un.shape), 1e-4, 1).astype(np.float32)
+    a, b = sn.solve(prn["x"], un, in_, xref_win=prn["xref_win"], xi=xi), on.solve(prn["x"], un, in_, xref_win=prn["xref_win"], xi=xi)
+    rc = np.abs(a[2][:, 6] - b[2][:, 6]) / np.abs(b[2][:, 6])
+    assert np.median(rc) <= 1e-4 and rc.max() <= 2e-2 and np.abs(a[2][:, 5] - b[2][:, 5]).max() <= 1e-4 * np.abs(b[2][:, 5]).max()
+    # a non-finite state is reported per problem (opt_cost = inf), never an abort, and does not disturb its CTA neighbours
+    xb = prn["x"].copy()
+    xb[3, 0] = np.nan
+    c = sn.solve(xb, un, in_, xref_win=prn["xref_win"], xi=xi)
+    assert np.isinf(c[2][3, 6]) and c[2][3, 2] == 1 and np.all(np.isfinite(np.delete(c[2][:, 6], 3)))
+    assert np.array_equal(np.delete(c[0], 3, axis=0), np.delete(a[0], 3, axis=0))
     # what the tensor-core solve does not implement is refused, never served by another path
     cfgr, blobr, _ = make_setup("iris", "pos", tensor=True)
     assert cfgr.u_slew_constr_coeff != 0.0
