@@ -233,6 +233,10 @@ int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args);
  * destinations (cudaHostRegister'ed, e.g. every rank's slice of a shared-memory result array in the multi-GPU gather);
  * pageable destinations work but are slower than sdempc_fetch. */
 int sdempc_fetch_direct(sdempc_t* h, const sdempc_solve_args* args);
+/* Page-lock / release a caller-owned host range for sdempc_fetch_direct (cudaHostRegister / cudaHostUnregister on the current
+ * device's context; a failure leaves no sticky CUDA error and the caller keeps using sdempc_fetch). */
+int sdempc_host_register(void* p, size_t nbytes);
+int sdempc_host_unregister(void* p);
 
 /* CUDA-event duration (ms) of the most recent kernel launch of this handle, on its own stream. */
 float sdempc_last_launch_ms(const sdempc_t* h);

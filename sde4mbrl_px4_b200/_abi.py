@@ -87,7 +87,7 @@ class SolveArgs(C.Structure):
 HEADER_SYMBOLS = [
     "sdempc_create", "sdempc_set_trajectory", "sdempc_state_from_traj", "sdempc_reset",
     "sdempc_solve_ex", "sdempc_solve", "sdempc_rollout", "sdempc_closed_loop", "sdempc_stage",
-    "sdempc_launch_timed", "sdempc_sync", "sdempc_device_out", "sdempc_fetch", "sdempc_fetch_direct", "sdempc_launch_count", "sdempc_last_launch_ms", "sdempc_kernel_info", "sdempc_probe_fp32",
+    "sdempc_launch_timed", "sdempc_sync", "sdempc_device_out", "sdempc_fetch", "sdempc_fetch_direct", "sdempc_host_register", "sdempc_host_unregister", "sdempc_launch_count", "sdempc_last_launch_ms", "sdempc_kernel_info", "sdempc_probe_fp32",
     "sdempc_destroy", "sdempc_last_error", "sdempc_version",
 ]
 
@@ -128,6 +128,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.sdempc_device_out.argtypes = [vp, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.sdempc_fetch.argtypes = [vp, C.POINTER(SolveArgs)]
     lib.sdempc_fetch_direct.argtypes = [vp, C.POINTER(SolveArgs)]
+    lib.sdempc_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.sdempc_host_unregister.argtypes = [C.c_void_p]
     lib.sdempc_launch_count.argtypes = [vp]
     lib.sdempc_launch_count.restype = C.c_int64
     lib.sdempc_last_launch_ms.argtypes = [vp]

@@ -805,6 +805,26 @@ int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args) {
     return fetch_solve(h, args);
 }
 
+int sdempc_host_register(void* p, size_t nbytes) {
+    if (!p || nbytes == 0) return fail(SDEMPC_EINVAL, "null range");
+    const cudaError_t e = cudaHostRegister(p, nbytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();   // leave no sticky error behind: the caller falls back to staged copies
+        return fail(SDEMPC_ECUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int sdempc_host_unregister(void* p) {
+    if (!p) return fail(SDEMPC_EINVAL, "null range");
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(SDEMPC_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 int sdempc_fetch_direct(sdempc_t* h, const sdempc_solve_args* args) {
     if (!h || !args) return fail(SDEMPC_EINVAL, "null argument");
     if (!args->x_evol || !args->u_plan || !args->info) return fail(SDEMPC_EINVAL, "x_evol, u_plan and info are required");

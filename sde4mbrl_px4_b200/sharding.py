@@ -121,7 +121,7 @@ class SharedResults:
     the concatenated [B_total, ...] arrays without another copy.  Two generations alternate, so the arrays returned by one
     call stay intact while the next call is being written.  All ranks construct it collectively (one node)."""
 
-    def __init__(self, shapes: dict):
+    def __init__(self, shapes: dict, register: bool = False):
         import torch.distributed as dist
         from multiprocessing import shared_memory
 
@@ -143,20 +143,21 @@ class SharedResults:
                     pass
             self._segs.append(segs)
             self.arrays.append({k: np.ndarray((self.world,) + tuple(sh), np.float32, buffer=sg.buf) for (k, sh), sg in zip(shapes.items(), segs)})
-        # page-lock this rank's own slices so that the device-to-host copy goes straight into them (sdempc_fetch_direct)
-        self.registered = False
-        try:
-            import torch
-            if torch.cuda.is_available():
-                rt = torch.cuda.cudart()
-                ok = True
-                for arrs in self.arrays:
-                    for a in arrs.values():
-                        sl = a[self.rank]
-                        ok = ok and int(rt.cudaHostRegister(sl.ctypes.data, sl.nbytes, 0)) == 0
-                self.registered = ok
-        except Exception:
-            self.registered = False
+        # page-lock this rank's own slices so that the device-to-host copy goes straight into them (sdempc_fetch_direct);
+        # registered ranges are released in close() -- a later mapping may reuse the addresses
+        self.registered, self._locked = False, []
+        if register:
+            from . import _abi
+            lib = _abi.load_library()
+            ok = True
+            for arrs in self.arrays:
+                for a in arrs.values():
+                    sl = a[self.rank]
+                    if lib.sdempc_host_register(sl.ctypes.data, sl.nbytes) == 0:
+                        self._locked.append(sl.ctypes.data)
+                    else:
+                        ok = False
+            self.registered = ok
         dist.barrier()
         if self.rank == 0:       # the mappings stay valid; the names disappear at once so nothing leaks if a rank dies
             for segs in self._segs:
@@ -166,6 +167,30 @@ class SharedResults:
     def next(self) -> dict:
         self.gen ^= 1
         return self.arrays[self.gen]
+
+    def close(self):
+        """Release the page locks and the mappings (rank-local; the segments themselves were unlinked at creation)."""
+        if self._locked:
+            from . import _abi
+            lib = _abi.load_library()
+            for p in self._locked:
+                lib.sdempc_host_unregister(p)
+            self._locked = []
+        self.registered = False
+        self.arrays = []
+        for segs in self._segs:
+            for sg in segs:
+                try:
+                    sg.close()
+                except Exception:
+                    pass
+        self._segs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int, gather: str = "shm"):
@@ -192,11 +217,13 @@ def solve_sharded(solver, local_problem: dict, u0, info0, B_total: int, gather: 
     ptr, nbytes, layout = solver.device_out()
     key = (gather, world, tuple((k, off, shape) for k, (off, shape) in sorted(layout.items())))
     if _gather_cache.get("key") != key:
+        if _gather_cache.get("shared") is not None:
+            _gather_cache["shared"].close()
         _gather_cache.clear()
         _gather_cache["key"] = key
         _gather_cache["bufs"] = {}
         if gather == "shm":
-            _gather_cache["shared"] = SharedResults({k: shape for k, (off, shape) in layout.items()})
+            _gather_cache["shared"] = SharedResults({k: shape for k, (off, shape) in layout.items()}, register=True)
     if gather == "shm":
         arrs = _gather_cache["shared"].next()
         solver.fetch_into(arrs["u"][rank], arrs["x_evol"][rank], arrs["info"][rank], direct=_gather_cache["shared"].registered)

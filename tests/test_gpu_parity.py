@@ -800,7 +800,13 @@ def test_solve_sharded_two_gpus_matches_the_oracle(O):
                     assert np.array_equal(g["u"], uo) and np.array_equal(g["x_evol"], xo) and np.array_equal(g["info"][:, :7], io[:, :7]), mode
                 else:
                     assert g is None
+        # a second batch size replaces the cached (page-locked) result buffers: the old ones must be released first
+        half = {{k: v[: v.shape[0] // 2] for k, v in loc.items()}}
+        nh = half["x"].shape[0]
+        g = sharding.solve_sharded(s, half, u0[:nh], i0[:nh], w * nh)
         if r == 0:
+            lo0 = 0
+            assert np.array_equal(g["u"][:nh], uo[:nh]) and g["u"].shape[0] == w * nh
             print("SHARDED_OK")
         dist.barrier(); dist.destroy_process_group()
     """)
