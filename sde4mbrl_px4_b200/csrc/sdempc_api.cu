@@ -77,7 +77,7 @@ static const std::vector<KernelChoice>& choices() {
         };
         for (auto& k : c)
             if (const TCKernels* t = tc_kernels(k.nu, k.W)) {   // one set of tensor-core kernels per (nu, width): the particle count is a run-time row mapping
-                k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve;
+                k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve; k.solve_tc_lat = t->solve_lat;
                 k.tc_bytes = t->bytes; k.tc_bytes_grad = t->bytes_grad; k.tc_bytes_solve = t->bytes_solve;
                 k.tc_tape_granules = t->tape_granules; k.tc_solve_tape_granules = t->solve_tape_granules; k.tc_cols = t->cols;
             }
@@ -122,11 +122,11 @@ struct sdempc_handle {
     int sm_count = 0;
     int64_t launches = 0;
     int last_grid = 0;
-    int regs = 0;
+    int regs = 0, regs_tc = 0, regs_tc_lat = 0;
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_tc = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_tc = false, staged_tc_lat = false;
     float last_ms = 0.f;
 };
 
@@ -356,6 +356,10 @@ static int ensure_device(sdempc_handle* h) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_grad));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
+        cudaFuncAttributes ft;
+        CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc)); h->regs_tc = ft.numRegs;
+        CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc_lat)); h->regs_tc_lat = ft.numRegs;
         CUDA_TRY(cudaMalloc(&h->d_wimg_tc, h->wimg_tc.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_wimg_tc, h->wimg_tc.data(), h->wimg_tc.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -398,21 +402,31 @@ static bool use_group(const sdempc_handle* h, int B) {
     return B > per_sm * h->sm_count;
 }
 
-// Tensor-core solve (SDEMPC_F_TENSOR): problems per CTA.  A CTA has NT = 128 / P rollout slots.  Measured (iris, 200
-// iterations): a CTA alone on its SM is latency bound (2.5 us per step evaluation), two CTAs on an SM slow each other
-// 1.4x, four 1.8x; NT / 4 problems per CTA need two line-search passes per iteration (80 step evaluations), NT problems
-// about three plus a full-width gradient pass (100).  4096 problems: 28 per CTA on 147 SMs 40.0 ms, 14 per CTA (two CTAs
-// per SM, one line-search pass) 42.7 ms, 7 per CTA 53.3 ms; 16 384 problems: 32 per CTA (512 CTAs) 56.4 ms, 64 per CTA
-// 61.2 ms, 128 per CTA 74.5 ms.  So: one CTA per SM with up to NT / 4 problems, then more CTAs per SM at NT / 4 problems
-// until the SMs are full (512 / columns resident CTAs), and only then more problems per CTA.
-static int tcs_problems_per_cta(const sdempc_handle* h, int B) {
+// Tensor-core solve (SDEMPC_F_TENSOR): problems per CTA and which build of the kernel.  A CTA has NT = 128 / P rollout slots.
+// Measured (iris, 200 iterations): a CTA alone on its SM is latency bound (2.5 us per step evaluation), two CTAs on an SM slow
+// each other 1.4x, four 1.8x; NT / 4 problems per CTA need two line-search passes per iteration at most (one in 97 % of the
+// iterations), NT problems about three plus a full-width gradient pass.  The build with the register budget of two CTAs per SM
+// (164 registers, no spill) is 11 % faster per CTA than the four-CTA build (128 registers): 4096 problems 35.8 against 40.1 ms,
+// 8192: 40.4 / 45.8, 16 384: 53.8 / 59.0, 32 768: 74.9 / 79.5, but 65 536 (two waves at two CTAs per SM): 139 / 111.
+// So: one CTA per SM with up to NT / 4 problems; then two CTAs per SM, growing the CTAs up to NT problems (two-CTA build);
+// beyond 2 x SMs x NT problems the four-CTA build with the SMs filled at NT / 4 problems per CTA first.
+static int tcs_problems_per_cta(const sdempc_handle* h, int B, bool* lat_build) {
     const int P = h->cfg.num_particles, NT = 128 / P;
-    if (h->tcs_ppc_override > 0) return std::min(h->tcs_ppc_override, NT);
+    const int max_res = 512 / std::max(1, h->kc.tc_cols);           // resident CTAs per SM tensor memory allows (4 or 2)
     const int base = std::max(1, NT / 4);
-    const int resident = h->sm_count * (512 / std::max(1, h->kc.tc_cols));
-    int ppc = (B + h->sm_count - 1) / h->sm_count;                 // one CTA per SM
-    if (ppc > base) ppc = std::max(base, (B + resident - 1) / resident);   // fill the SMs at NT / 4 problems per CTA, then grow
-    return std::max(1, std::min(ppc, NT));
+    *lat_build = true;
+    if (h->tcs_ppc_override > 0) {
+        const int ppc = std::min(h->tcs_ppc_override, NT);
+        *lat_build = (B + ppc - 1) / ppc <= 2 * h->sm_count;
+        return ppc;
+    }
+    int ppc = (B + h->sm_count - 1) / h->sm_count;                  // one CTA per SM
+    if (ppc <= base) return std::max(1, ppc);
+    ppc = std::max(base, (B + 2 * h->sm_count - 1) / (2 * h->sm_count));   // two CTAs per SM, growing
+    if (ppc <= NT) return ppc;
+    *lat_build = false;                                              // large batch: all the CTAs tensor memory allows
+    const int resident = h->sm_count * max_res;
+    return std::max(1, std::min(std::max(base, (B + resident - 1) / resident), NT));
 }
 
 static int ensure_tcs_ws(sdempc_handle* h, int grid, int rs) {
@@ -523,7 +537,8 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     const bool spec = !tcs && use_spec(h, B), group = !tcs && use_group(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
     const bool cl = !tcs && use_cluster(h, B), pcl = !tcs && use_pcluster(h, B);
-    const int ppc = tcs ? tcs_problems_per_cta(h, B) : 0, rs = 128;   // TCS_RS (mpc_tcsolve.cuh)
+    bool tcs_lat = false;
+    const int ppc = tcs ? tcs_problems_per_cta(h, B, &tcs_lat) : 0, rs = 128;   // TCS_RS (mpc_tcsolve.cuh)
     const int grid = tcs ? (B + ppc - 1) / ppc : pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
     if (tcs) { if ((rc = ensure_tcs_ws(h, grid, rs))) return rc; }
@@ -559,7 +574,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
     if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; k.tcs_sms = h->sm_count; }
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl;
-    h->staged_tc = tcs;
+    h->staged_tc = tcs; h->staged_tc_lat = tcs && tcs_lat;
     return 0;
 }
 
@@ -582,7 +597,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
     }
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
-    const bool tcs = (fn == h->kc.solve_tc) && fn != nullptr;
+    const bool tcs = (fn == h->kc.solve_tc || fn == h->kc.solve_tc_lat) && fn != nullptr;
     const int threads = tcs ? 128 : spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     const size_t smem = tcs ? (size_t)h->kc.tc_bytes_solve : spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
     void* args[] = {const_cast<KParams*>(&k)};
@@ -592,7 +607,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
 }
 
 static void (*staged_kernel(const sdempc_handle* h))(KParams) {
-    return h->staged_tc ? h->kc.solve_tc : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
+    return h->staged_tc ? (h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
            : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
@@ -1010,7 +1025,7 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
     if (h->staged_tc) {
-        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->regs; out[4] = h->last_grid; out[5] = h->sm_count;
+        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
         return 0;
     }
     out[0] = (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;

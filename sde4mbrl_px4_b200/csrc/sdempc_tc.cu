@@ -18,8 +18,11 @@ __global__ void __launch_bounds__(128, 512 / TCLayout<NU, W>::COLS) mpc_tc_rollo
     tc_rollout_body<NU, W, GRAD>(P, tc_smem, &tmem_slot, tc_bar);
 }
 
-template <int NU, int W>
-__global__ void __launch_bounds__(128, 512 / TCLayout<NU, W>::COLS) mpc_tc_solve_kernel(const __grid_constant__ KParams P) {
+// MINB = resident CTAs per SM the register budget is set for.  Two builds of the width-32 solve: 4 CTAs per SM (128 registers,
+// what tensor memory allows: large batches) and 2 CTAs per SM (164 registers, no spill: 11 % faster per CTA, used while the
+// batch needs at most two CTAs per SM).
+template <int NU, int W, int MINB>
+__global__ void __launch_bounds__(128, MINB) mpc_tc_solve_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t tc_bars[2];
@@ -33,7 +36,8 @@ static TCKernels make_tc() {
     TCKernels k;
     k.rollout = mpc_tc_rollout_kernel<NU, W, false>;
     k.rollout_grad = mpc_tc_rollout_kernel<NU, W, true>;
-    k.solve = mpc_tc_solve_kernel<NU, W>;
+    k.solve = mpc_tc_solve_kernel<NU, W, 512 / L::COLS>;
+    k.solve_lat = (512 / L::COLS > 2) ? mpc_tc_solve_kernel<NU, W, 2> : k.solve;
     // Residency must be bounded by tensor memory (512 / COLS CTAs per SM), never exceed it: a CTA that the block
     // scheduler places beyond that spins in tcgen05.alloc while holding its slot (width 64, forward variant:
     // registers and shared memory allowed three CTAs, tensor memory two -- launches were bimodal, 0.30 / 0.41 ms).

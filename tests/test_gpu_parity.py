@@ -415,7 +415,7 @@ def test_tensor_core_solve_modes_and_batches(solver, O):
     s, o = solver.MPCSolver(cfg, blob), O.Oracle(cfg_f, blob, "f32")
     tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.0, duration=20.0))
     s.set_trajectory(tab); o.set_trajectory(tab)
-    for B in (1, 5, 200, 148 * 128 + 77):
+    for B in (1, 5, 200, 148 * 128 + 77, 296 * 128 + 5):     # the last one is past what two CTAs per SM hold: the four-CTA build
         x = tab[0:1, 1:] + 0.05 * np.random.default_rng(B).standard_normal((B, 13)).astype(np.float32)
         x[:, 6:10] /= np.linalg.norm(x[:, 6:10], axis=1, keepdims=True)
         ct = np.linspace(0, 3, B).astype(np.float32)
@@ -434,9 +434,13 @@ def test_tensor_core_solve_modes_and_batches(solver, O):
             assert np.median(np.abs(up - upo).reshape(B, -1).max(axis=1)) <= 1e-4
             assert np.abs(xe - xeo)[:nchk].max() <= 2e-2
         ki = s.kernel_info()
-        ppc = -(-B // ki["sm_count"])                 # one CTA per SM up to 32 problems, then fill the SMs (4 CTAs each), then grow
-        ppc = ppc if ppc <= 32 else min(128, max(32, -(-B // (4 * ki["sm_count"]))))
+        ppc = -(-B // ki["sm_count"])                 # one CTA per SM up to 32 problems, then two per SM growing to 128 problems
+        ppc = ppc if ppc <= 32 else max(32, -(-B // (2 * ki["sm_count"])))   # (the build with two CTAs' registers) ...
+        lat = ppc <= 128
+        if not lat:                                   # ... then the four-CTA build, SMs filled at 32 problems per CTA first
+            ppc = min(128, max(32, -(-B // (4 * ki["sm_count"]))))
         assert ki["problems_per_cta"] == ppc and ki["ctas"] == -(-B // ppc), (B, ki)
+        assert (ki["regs_per_thread"] > 128) == lat, (B, ki)
     # set-point mode and early stopping with the YAML tolerances
     cfgp, blobp, _ = make_setup("iris", "traj", tensor=True)   # set-point mode: xdes instead of a trajectory time
     sp, op = solver.MPCSolver(cfgp, blobp), O.Oracle(make_setup("iris", "traj")[0], blobp, "f32")
