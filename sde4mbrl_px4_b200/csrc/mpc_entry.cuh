@@ -31,6 +31,7 @@ struct KernelChoice {
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
     void (*solve_tc)(KParams);     // tensor-core batched APG solve, SDEMPC_F_TENSOR
+    void (*solve_tc_spec)(KParams);// ... with the speculative gradient pass (few problems per CTA)
     void (*solve_tc_lat)(KParams); // ... built for two CTAs per SM (more registers): small and medium batches
     int tc_bytes, tc_bytes_grad, tc_tape_granules, tc_bytes_solve, tc_solve_tape_granules, tc_cols;
     int gp;
@@ -557,7 +558,7 @@ KernelChoice make_choice() {
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     k.solve_pc = nullptr;
-    k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = nullptr;
+    k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
     k.gp = group_gp(NU, W);

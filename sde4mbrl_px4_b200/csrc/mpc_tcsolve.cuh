@@ -32,7 +32,7 @@ namespace sdempc {
 // kernel's instructions were address arithmetic); rows beyond the CTA's problems are never touched
 constexpr int TCS_RS = 128;
 struct TCSWs {
-    int RS, n, o_xk, o_yk, o_g, o_uprev, o_x0, o_xref, o_xi, o_tape, total;
+    int RS, n, o_xk, o_yk, o_g, o_uprev, o_x0, o_xref, o_xi, o_xh, o_tape, total;
 };
 __host__ __device__ inline TCSWs tcs_ws_layout(int H, int NU, int RS, int TG) {
     TCSWs w;
@@ -45,6 +45,7 @@ __host__ __device__ inline TCSWs tcs_ws_layout(int H, int NU, int RS, int TG) {
     w.o_x0 = o; o += 16 * RS;
     w.o_xref = o; o += (H + 1) * NX * RS;
     w.o_xi = o; o += H * 6 * 128;                 // indexed by slot row (q * P + p) < 128
+    w.o_xh = o; o += 16 * 128;                    // x_H of the rows that recorded a tape (speculative build), by slot row
     w.o_tape = o; o += H * TG * 128 * 4;          // adjoint tape of the GRAD rows: [step][granule][row] float4
     w.total = o;
     return w;
@@ -67,6 +68,11 @@ struct TCSShared {
     float t_J[128], t_dec[128];
     short t_q[128], t_j[128];
     int ntasks;
+    // speculative build (SPECG): phase of every problem, kind of every task, the slot row that holds a problem's tape
+    float fy_next[128];
+    short trow[128], b_q[128], scnt[128], firstT[128];
+    int wsumL[4];
+    unsigned char ph[128], t_kind[128], smask[128];
 };
 
 namespace tc {
@@ -83,7 +89,24 @@ __device__ __forceinline__ void softplus_sigmoid_fast(float s, float& sp, float&
 }  // namespace tc
 
 // Body of the solve kernel.  sB: weight image (TCLayout, forward + adjoint parts).  bars[0]: weight staging, bars[1]: MMA.
-template <int NU, int W>
+// SPECG = true: the build for CTAs with few problems (PPC <= slots / 8), where most slots would idle.
+//   (1) SPECULATIVE GRADIENT PASSES.  Next to the line-search trials the free slots run the forward pass of the NEXT gradient
+//       evaluation for the likely outcomes, recording a tape each: "R" at x_k, where a rejected step restarts from (30 % of
+//       the iterations of the benchmark problems end that way, and x_k is known before the search), and one per trial j at
+//       the y_{k+1} that trial gives if accepted (the expressions of plan_update, hence the same bits).  When the outcome has
+//       a tape, the iteration's gradient needs only the adjoint sweep: two passes per iteration instead of three.
+//   (2) PER-PROBLEM PHASES.  A CTA-wide state would make all problems pay for the one whose outcome had no tape.  So each
+//       problem carries its own phase (0 needs the gradient's forward pass, 1 line search, 2 tape ready, 3 done); every loop
+//       turn runs one forward pass over whatever forward tasks exist (gradient passes, trials, speculations, mixed) and
+//       then one adjoint sweep over the problems whose tape is ready, each in the slot that recorded it.  A miss costs that
+//       problem one extra turn, nobody else.
+//   Problems are independent, every task evaluates the same expressions on the same operands as in the other build, and
+//   a tensor-memory lane's result does not depend on which lane it is: the two builds return identical bits
+//   (tests/test_gpu_parity.py::test_tensor_core_solve_speculative_build_returns_the_same_bits).
+//   Measured (iris, 200 iterations, one CTA per SM): 7 problems per CTA 35.8 -> 27.7 ms, 14 per CTA 34.1 -> 29 ms.  With 28
+//   per CTA (two trials + R + one speculation each) the passes themselves get 1.3x slower — four warps of rows with
+//   distinct operands instead of one, twice the tape — and the build loses (36.8 against 35.9 ms): hence PPC <= slots / 8.
+template <int NU, int W, bool SPECG>
 __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* sB, uint32_t* tmem_base_slot, uint64_t* bars,
                                               TCSShared& sh) {
     using L = TCSLayout<NU, W>;
@@ -129,12 +152,15 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
     float* X0 = wsb + ws.o_x0;
     float* XREF = wsb + ws.o_xref;
     float* XI = wsb + ws.o_xi;
+    [[maybe_unused]] float* XH = wsb + ws.o_xh + tid;
     float4* tape = reinterpret_cast<float4*>(wsb + ws.o_tape) + tid;
     auto tp = [&](int t, int g) -> float4* { return tape + ((size_t)t * L::STG + g) * 128; };
     // the tape is written once and read once per iteration: streaming stores / loads (evict first), so that it does not
     // push the plans, the reference window and the noise of the resident CTAs out of L2
     const bool lone_cta = gridDim.x <= (unsigned)P.tcs_sms;   // one CTA per SM: the next step's tape fits L1, prefetch that far
-    auto stt = [&](int t, int g, float4 v) { if (lone_cta) *tp(t, g) = v; else __stcs(tp(t, g), v); };
+    // (the speculative build records several tapes per problem and reads one: streaming there too)
+    const bool lone_tape = lone_cta && !SPECG;
+    auto stt = [&](int t, int g, float4 v) { if (lone_tape) *tp(t, g) = v; else __stcs(tp(t, g), v); };
     constexpr int RS = TCS_RS;
     const int n = ws.n;
     const bool enu = (P.flags & SDEMPC_F_FRAME_ENU) != 0;
@@ -177,8 +203,10 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
         sh.Jx[q] = 0.f; sh.fy[q] = 0.f; sh.gsq[q] = 0.f; sh.sum_ls[q] = 0.f; sh.sum_s[q] = 0.f; sh.init_cost[q] = 0.f; sh.Jp[q] = 0.f;
         sh.k[q] = 1; sh.no_imp[q] = 0; sh.it[q] = 0; sh.n_ls[q] = 0; sh.jn[q] = 0;
         sh.active[q] = 1; sh.need[q] = 0; sh.ok[q] = 0;
+        sh.ph[q] = 0;
     } else {
         sh.active[tid] = 0; sh.need[tid] = 0;
+        sh.ph[tid] = 3;
     }
     for (int idx = tid; idx < nq * (P.H + 1); idx += 128) {
         const int q = idx / (P.H + 1), t = idx - q * (P.H + 1);
@@ -213,6 +241,69 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
     const float* bias2 = reinterpret_cast<const float*>(sB + L::BIAS2);
     const float* bias3 = reinterpret_cast<const float*>(sB + L::BIAS3);
 
+    // plan update after a resolved line search (acc: 1 accept, 0 reject = restart from x_k, 2 untouched), all threads
+    auto plan_update = [&]() {
+        // plans: thread -> (problem oq = tid mod 2^k, part): consecutive threads touch consecutive problems (coalesced),
+        // a problem's entries are split over 128 / 2^k threads; four independent entries are in flight per thread
+        int npad = 1;
+        while (npad < nq) npad <<= 1;
+        const int oq = tid & (npad - 1), part = tid / npad, nparts = 128 / npad;
+        const int a = oq < nq ? (int)sh.acc[oq] : 2;
+        if (a != 2) {
+            const float sq = sh.s[oq];
+            const int kq = sh.k[oq];
+            const float beta = apg_momentum_tab(P, kq);
+            for (int i0 = part; i0 < n; i0 += 4 * nparts) {
+                float xkv[4], yv[4], gv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * nparts;
+                    if (i < n) {
+                        xkv[j] = XK[i * RS + oq];
+                        if (a == 1) { yv[j] = YK[i * RS + oq]; gv[j] = G[i * RS + oq]; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * nparts;
+                    if (i < n) {
+                        const int ii = i % NU;
+                        if (a == 1) {
+                            const float xv = clipf(fma_(-sq, gv[j], yv[j]), P.u_lo[ii], P.u_hi[ii]);
+                            YK[i * RS + oq] = clipf(fma_(beta, xv - xkv[j], xv), P.u_lo[ii], P.u_hi[ii]);
+                            XK[i * RS + oq] = xv;
+                        } else {
+                            YK[i * RS + oq] = xkv[j];
+                        }
+                    }
+                }
+            }
+        }
+    };
+    // owner bookkeeping of problem oq after its line search: accept / reject, momentum counter, trace, stop tests
+    auto bookkeeping = [&](int oq) {
+        const float s = sh.s[oq], Jp = sh.Jp[oq], Jx0 = sh.Jx[oq];
+        sh.sum_ls[oq] += (float)sh.n_ls[oq];
+        sh.sum_s[oq] += s;
+        const bool accept = sh.acc[oq] == 1;
+        bool converged = false;
+        if (accept) {
+            sh.Jx[oq] = Jp; sh.k[oq] += 1; sh.no_imp[oq] = 0;
+            const float tol = P.atol + P.rtol * fabsf(Jx0);
+            converged = (fabsf(Jx0 - Jp) <= tol) || (Jp <= P.atol);
+        } else {
+            sh.k[oq] = 1; sh.no_imp[oq] += 1;
+        }
+        const int it = sh.it[oq];
+        if (P.trace != nullptr) {
+            float* tr = P.trace + ((size_t)(b0 + oq) * P.max_iter + (it - 1)) * SDEMPC_TRACE_W;
+            tr[0] = sh.fy[oq]; tr[1] = Jp; tr[2] = s; tr[3] = (float)sh.n_ls[oq]; tr[4] = accept ? 1.f : 0.f; tr[5] = sh.Jx[oq];
+            tr[6] = sh.gsq[oq]; tr[7] = (float)sh.k[oq];
+        }
+        const float fyv = sh.fy[oq];
+        if (it >= P.max_iter || sh.no_imp[oq] >= P.max_no_improve || converged || !(fyv == fyv)) sh.active[oq] = 0;
+    };
+
     enum { S_GRAD = 0, S_LS = 1, S_FINAL = 2 };
     int state = S_GRAD;
     for (;;) {
@@ -220,13 +311,82 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
         int q = 0, pidx = tid % PP, mode = 2;
         bool valid = false;
         float s_t = 0.f;
-        if (state == S_GRAD) {
+        [[maybe_unused]] bool spec = false, tape_on = false, at_xk = false;
+        [[maybe_unused]] float beta_t = 0.f;
+        if constexpr (SPECG) {
+            // forward tasks of this turn: one gradient forward pass per problem in phase 0; trials (+ speculations) of the
+            // problems in phase 1 on the remaining slots
+            const int ph = tid < nq ? (int)sh.ph[tid] : 3;
+            const int n_gf = __syncthreads_count(ph == 0 ? 1 : 0);
+            const int cnt = __syncthreads_count(ph == 1 ? 1 : 0);
+            if (n_gf + cnt == 0) state = S_FINAL;          // every problem is done
+            else {
+                // A problem in its line search gets m slots: trials, and tape tasks for what may follow them — "R", the gradient
+                // pass at x_k that a REJECTED step restarts from (known before the search: 30 % of the iterations end that way),
+                // and speculations for the likeliest accepted trials (from the start of a search: trial 1 in 61 % of the
+                // iterations, trial 0 in 5 %, trial 2 in 4 %)
+                int mq = 0, nt = ph == 0 ? 1 : 0;
+                unsigned smask = 0;                      // bit i: trial j0 + i has a speculation
+                if (ph == 1) {
+                    const int m = (NT - n_gf) / cnt, j0 = sh.jn[tid], rem = P.maxls + 1 - j0;
+                    if (m < 4) mq = m < rem ? m : rem;                                // crowded: trials only
+                    else {
+                        mq = (m - m / 2) < rem ? (m - m / 2) : rem;
+                        nt = (m - mq) < (mq + 1) ? (m - mq) : (mq + 1);
+                        const bool from_start = j0 == 0 && mq >= 2;
+                        for (int r = 0; r < nt - 1; ++r) smask |= 1u << (from_start ? (r == 0 ? 1 : r == 1 ? 0 : r) : r);
+                    }
+                }
+                // slots: first every task that records a tape (gradient forward passes, speculations), then the trials — the
+                // tape rows in use stay contiguous (scattered rows touch every line of the tape region: 4x the L2 footprint)
+                int incT = nt, incL = mq;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int vT = __shfl_up_sync(0xffffffffu, incT, off), vL = __shfl_up_sync(0xffffffffu, incL, off);
+                    if (lane >= off) { incT += vT; incL += vL; }
+                }
+                if (lane == 31) { sh.wsum[warp] = incT; sh.wsumL[warp] = incL; }
+                __syncthreads();
+                int baseT = 0, baseL = 0, totT = 0;
+                for (int w = 0; w < 4; ++w) {
+                    if (w < warp) { baseT += sh.wsum[w]; baseL += sh.wsumL[w]; }
+                    totT += sh.wsum[w];
+                }
+                const int firstT = baseT + incT - nt, firstL = totT + baseL + incL - mq;
+                if (ph == 0) {
+                    sh.firstT[tid] = (short)firstT;
+                    sh.t_q[firstT] = (short)tid; sh.t_j[firstT] = 0; sh.t_kind[firstT] = 2;
+                } else if (ph == 1) {
+                    sh.first[tid] = firstL; sh.cnt[tid] = mq; sh.firstT[tid] = (short)firstT; sh.scnt[tid] = (short)nt; sh.smask[tid] = (unsigned char)smask;
+                    const int j0 = sh.jn[tid];
+                    for (int j = 0; j < mq; ++j) { sh.t_q[firstL + j] = (short)tid; sh.t_j[firstL + j] = (short)(j0 + j); sh.t_kind[firstL + j] = 0; }
+                    if (nt > 0) { sh.t_q[firstT] = (short)tid; sh.t_j[firstT] = 0; sh.t_kind[firstT] = 3; }
+                    for (int j = 0, r = 1; j < mq; ++j)
+                        if ((smask >> j) & 1u) { sh.t_q[firstT + r] = (short)tid; sh.t_j[firstT + r] = (short)(j0 + j); sh.t_kind[firstT + r] = 1; ++r; }
+                }
+                if (tid == 127) sh.ntasks = firstL + mq;
+                __syncthreads();
+                const int kslot = tid / PP;
+                valid = kslot < sh.ntasks;
+                q = valid ? (int)sh.t_q[kslot] : 0;
+                const int kind = valid ? (int)sh.t_kind[kslot] : 0;
+                mode = kind >= 2 ? 1 : 0;                // 2: gradient pass at y_k, 3: at x_k (restart), 1: speculation, 0: trial
+                spec = kind == 1;
+                at_xk = kind == 3;
+                tape_on = valid && kind != 0;
+                s_t = sh.s[q];
+                const int dj = (valid && kind < 2) ? (int)sh.t_j[kslot] - sh.jn[q] : 0;
+                for (int i = 0; i < dj; ++i) s_t = s_t * P.dec_f;
+                beta_t = apg_momentum_tab(P, sh.k[q]);
+            }
+        }
+        if (!SPECG && state == S_GRAD) {
             const int myq = tid / PP;
             const bool act = myq < nq && sh.active[myq];
             if (__syncthreads_or(act ? 1 : 0) == 0) { state = S_FINAL; }
             else { q = myq < nq ? myq : 0; valid = act; mode = 1; }
         }
-        if (state == S_LS) {
+        if (!SPECG && state == S_LS) {
             // compacted concurrent line search: deal the trials of the needy problems onto the slots (thread q = problem q)
             const bool nd = tid < nq && sh.need[tid];
             const int cnt = __syncthreads_count(nd ? 1 : 0);
@@ -237,68 +397,9 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     sh.acc[tid] = (sh.ok[tid] && (Jp <= sh.Jx[tid])) ? 1 : 0;
                 } else if (tid < 128) sh.acc[tid] = 2;     // 2: not an active problem, plans untouched
                 __syncthreads();
-                // plans: thread -> (problem oq = tid mod 2^k, part): consecutive threads touch consecutive problems (coalesced),
-                // a problem's entries are split over 128 / 2^k threads; four independent entries are in flight per thread
-                {
-                    int npad = 1;
-                    while (npad < nq) npad <<= 1;
-                    const int oq = tid & (npad - 1), part = tid / npad, nparts = 128 / npad;
-                    const int a = oq < nq ? (int)sh.acc[oq] : 2;
-                    if (a != 2) {
-                        const float sq = sh.s[oq];
-                        const int kq = sh.k[oq];
-                        const float beta = apg_momentum_tab(P, kq);
-                        for (int i0 = part; i0 < n; i0 += 4 * nparts) {
-                            float xkv[4], yv[4], gv[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int i = i0 + j * nparts;
-                                if (i < n) {
-                                    xkv[j] = XK[i * RS + oq];
-                                    if (a == 1) { yv[j] = YK[i * RS + oq]; gv[j] = G[i * RS + oq]; }
-                                }
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int i = i0 + j * nparts;
-                                if (i < n) {
-                                    const int ii = i % NU;
-                                    if (a == 1) {
-                                        const float xv = clipf(fma_(-sq, gv[j], yv[j]), P.u_lo[ii], P.u_hi[ii]);
-                                        YK[i * RS + oq] = clipf(fma_(beta, xv - xkv[j], xv), P.u_lo[ii], P.u_hi[ii]);
-                                        XK[i * RS + oq] = xv;
-                                    } else {
-                                        YK[i * RS + oq] = xkv[j];
-                                    }
-                                }
-                            }
-                        }
-                    }
-                }
+                plan_update();
                 __syncthreads();   // sh.k is read above, updated below
-                if (tid < nq && sh.active[tid]) {
-                    const int oq = tid;
-                    const float s = sh.s[oq], Jp = sh.Jp[oq], Jx0 = sh.Jx[oq];
-                    sh.sum_ls[oq] += (float)sh.n_ls[oq];
-                    sh.sum_s[oq] += s;
-                    const bool accept = sh.acc[oq] == 1;
-                    bool converged = false;
-                    if (accept) {
-                        sh.Jx[oq] = Jp; sh.k[oq] += 1; sh.no_imp[oq] = 0;
-                        const float tol = P.atol + P.rtol * fabsf(Jx0);
-                        converged = (fabsf(Jx0 - Jp) <= tol) || (Jp <= P.atol);
-                    } else {
-                        sh.k[oq] = 1; sh.no_imp[oq] += 1;
-                    }
-                    const int it = sh.it[oq];
-                    if (P.trace != nullptr) {
-                        float* tr = P.trace + ((size_t)(b0 + oq) * P.max_iter + (it - 1)) * SDEMPC_TRACE_W;
-                        tr[0] = sh.fy[oq]; tr[1] = Jp; tr[2] = s; tr[3] = (float)sh.n_ls[oq]; tr[4] = accept ? 1.f : 0.f; tr[5] = sh.Jx[oq];
-                        tr[6] = sh.gsq[oq]; tr[7] = (float)sh.k[oq];
-                    }
-                    const float fyv = sh.fy[oq];
-                    if (it >= P.max_iter || sh.no_imp[oq] >= P.max_no_improve || converged || !(fyv == fyv)) sh.active[oq] = 0;
-                }
+                if (tid < nq && sh.active[tid]) bookkeeping(tid);
                 __syncthreads();   // plans and flags visible to the rows of the next pass
                 state = S_GRAD;
                 continue;
@@ -342,8 +443,9 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             mode = 2;
         }
         // ================= forward rollout of my task (all 128 threads in lockstep) =================
-        const float* useq = (mode == 2) ? XK : YK;
-        const int xi_row = q * PP + pidx;
+        const float* useq = (mode == 2 || (SPECG && at_xk)) ? XK : YK;
+        int xi_row = q * PP + pidx;
+        const bool tape_w = SPECG ? tape_on : (mode == 1 && valid);
         float x[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) x[i] = X0[i * RS + q];
@@ -358,6 +460,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
         float Jp = 0.f, disc = 1.f, dec = 0.f;
         const float* yq = useq + q;
         const float* gq = G + q;
+        [[maybe_unused]] const float* xkq = XK + q;
         const float* xiq = XI + xi_row;
         const float* xrq = XREF + q;
         for (int t = 0; t < P.H; ++t) {
@@ -373,6 +476,9 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     const float xv = clipf(fma_(-s_t, gv, yv), P.u_lo[i], P.u_hi[i]);
                     dec = fma_(gv, xv - yv, dec);
                     u[i] = xv;
+                    if constexpr (SPECG) {   // the y_{k+1} this trial gives if accepted: the expression of plan_update
+                        if (spec) u[i] = clipf(fma_(beta_t, xv - xkq[(t * NU + i) * RS], xv), P.u_lo[i], P.u_hi[i]);
+                    }
                 } else {
                     u[i] = yv;
                 }
@@ -387,6 +493,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                 for (int i = 0; i < NU; ++i) {
                     tc::prefetch_l1(yt + (NU + i) * RS);
                     if (mode == 0) tc::prefetch_l1(gt + (NU + i) * RS);
+                    if constexpr (SPECG) { if (spec) tc::prefetch_l1(xkq + ((t + 1) * NU + i) * RS); }
                 }
 #pragma unroll
                 for (int i = 0; i < 6; ++i) tc::prefetch_l1(xit + (6 + i) * 128);
@@ -420,7 +527,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = tc::tanh_approx(v[i]);
                 tc::st16(lane_addr + L::C_A + c0, v);
-                if (mode == 1 && valid) {
+                if (tape_w) {
                     stt(t, L::S_H1 + c0 / 8, tc::pack8(v));
                     stt(t, L::S_H1 + c0 / 8 + 1, tc::pack8(v + 8));
                 }
@@ -447,7 +554,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     v[i + 2] = tc::tanh_approx(v[i + 2] + bv.z); v[i + 3] = tc::tanh_approx(v[i + 3] + bv.w);
                 }
                 tc::st16(lane_addr + L::C_A + c0, v);
-                if (mode == 1 && valid) {
+                if (tape_w) {
                     stt(t, L::S_H2 + c0 / 8, tc::pack8(v));
                     stt(t, L::S_H2 + c0 / 8 + 1, tc::pack8(v + 8));
                 }
@@ -475,7 +582,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             }
             float xn[NX], rn;
             const float l = phys_step<NU>(P, t, x, u, up, r6, sig, xi, xr, xn, rn);
-            if (mode == 1 && valid) {
+            if (tape_w) {
                 stt(t, L::S_ST, make_float4(r6[0], r6[1], r6[2], sig[0]));
                 stt(t, L::S_ST + 1, make_float4(sig[1], sig[2], sig[3], sig[4]));
                 stt(t, L::S_ST + 2, make_float4(sig[5], dsg[0], dsg[1], dsg[2]));
@@ -509,7 +616,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
         }
         const float Jm = pmean(Jp);
         if (state == S_FINAL) break;
-        if (state == S_LS) {
+        if (!SPECG && state == S_LS) {
             const int kslot = tid / PP;
             if (valid && pidx == 0) { sh.t_J[kslot] = Jm; sh.t_dec[kslot] = dec; }
             __syncthreads();
@@ -534,6 +641,72 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             __syncthreads();
             continue;
         }
+        if constexpr (SPECG) {
+            // ---- results of the forward tasks; problems whose line search resolved: accept / reject, plans, stop tests ----
+            const int kslot = tid / PP;
+            if (valid && pidx == 0) { sh.t_J[kslot] = Jm; sh.t_dec[kslot] = dec; }
+            if (tape_on) {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) XH[i * 128] = x[i];
+            }
+            sh.b_q[tid] = -1;
+            __syncthreads();
+            if (tid < nq) {
+                const int oq = tid, ph = sh.ph[oq], f = sh.first[oq], fT = sh.firstT[oq];
+                unsigned char a = 2;
+                if (ph == 0) {                      // gradient forward pass done: its tape is in slot fT
+                    sh.fy[oq] = sh.t_J[fT]; sh.trow[oq] = (short)fT; sh.ph[oq] = 2;
+                } else if (ph == 1) {               // take the first passing trial in order, exactly as the sequential search
+                    const int c = sh.cnt[oq];
+                    float s = sh.s[oq];
+                    const float fy = sh.fy[oq];
+                    int jn = sh.jn[oq], isel = 0;
+                    bool ok = false;
+                    float Jsel = 0.f;
+                    for (int i = 0; i < c; ++i) {
+                        Jsel = sh.t_J[f + i];
+                        ok = (Jsel <= fma_(P.coef, sh.t_dec[f + i], fy));
+                        sh.n_ls[oq] = jn + 1;
+                        isel = i;
+                        if (ok) break;
+                        if (jn < P.maxls) s = s * P.dec_f;
+                        ++jn;
+                    }
+                    sh.s[oq] = s; sh.jn[oq] = jn; sh.Jp[oq] = Jsel; sh.ok[oq] = ok ? 1 : 0;
+                    if (ok || jn > P.maxls) {       // resolved
+                        a = (ok && (Jsel <= sh.Jx[oq])) ? 1 : 0;
+                        const unsigned sm = sh.smask[oq];
+                        int row = -1;                // the tape task that ran what this outcome needs next, if any
+                        if (a == 0) { if (sh.scnt[oq] > 0) row = fT; }
+                        else if ((sm >> isel) & 1u) row = fT + 1 + __popc(sm & ((1u << isel) - 1u));
+                        sh.trow[oq] = (short)row;
+                        if (row >= 0) sh.fy_next[oq] = sh.t_J[row];
+                    }
+                }
+                sh.acc[oq] = a;
+            } else sh.acc[tid] = 2;
+            __syncthreads();
+            plan_update();
+            __syncthreads();   // sh.k is read above, updated below
+            if (tid < nq && sh.acc[tid] != 2) {
+                const int oq = tid;
+                bookkeeping(oq);
+                if (!sh.active[oq]) sh.ph[oq] = 3;
+                else if (sh.trow[oq] >= 0) { sh.ph[oq] = 2; sh.fy[oq] = sh.fy_next[oq]; }   // speculation hit: sweep only
+                else sh.ph[oq] = 0;
+            }
+            __syncthreads();
+            // ---- adjoint sweep over the problems whose tape is ready, each in the slot that recorded it ----
+            const bool rdy = tid < nq && sh.ph[tid] == 2;
+            if (rdy) sh.b_q[sh.trow[tid]] = (short)tid;
+            if (__syncthreads_or(rdy ? 1 : 0) == 0) continue;
+            const int bq = (int)sh.b_q[kslot];
+            valid = bq >= 0;
+            q = valid ? bq : 0;
+            xi_row = q * PP + pidx;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) x[i] = valid ? XH[i * 128] : 0.f;
+        }
         // ================= GRAD: adjoint sweep on the tensor cores, gradient -> G (particle mean) =================
         {
             float lam[NX], gp[NU], xn[NX];
@@ -542,7 +715,7 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
 #pragma unroll
             for (int i = 0; i < NU; ++i) gp[i] = 0.f;
             float gsq = 0.f;
-            auto ldt = [&](int t, int g) -> float4 { return !valid ? make_float4(0.f, 0.f, 0.f, 0.f) : lone_cta ? *tp(t, g) : __ldcs(tp(t, g)); };
+            auto ldt = [&](int t, int g) -> float4 { return !valid ? make_float4(0.f, 0.f, 0.f, 0.f) : lone_tape ? *tp(t, g) : __ldcs(tp(t, g)); };
             for (int t = P.H - 1; t >= 0; --t) {
                 if (t > 0 && valid) {   // the sweep consumes its tape as it loads it: pull the previous step's granules towards the SM now
 #pragma unroll
@@ -666,11 +839,15 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
 #pragma unroll
                 for (int i = 0; i < NX; ++i) xn[i] = xt[i];
             }
-            if (valid && pidx == 0) { sh.fy[q] = Jm; sh.gsq[q] = gsq; }
+            if (valid && pidx == 0) {
+                if constexpr (!SPECG) sh.fy[q] = Jm;       // (the speculative build set it when the forward task resolved)
+                sh.gsq[q] = gsq;
+            }
         }
         __syncthreads();
-        if (tid < nq && sh.active[tid]) {   // thread q = problem q: open this iteration's line search
+        if (tid < nq && sh.active[tid] && (!SPECG || sh.ph[tid] == 2)) {   // thread q = problem q: open this iteration's line search
             const int oq = tid;
+            if constexpr (SPECG) sh.ph[oq] = 1;
             const int it = sh.it[oq] + 1;
             sh.it[oq] = it;
             if (it == 1) { sh.Jx[oq] = sh.fy[oq]; sh.init_cost[oq] = sh.fy[oq]; }

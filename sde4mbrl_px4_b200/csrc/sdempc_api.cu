@@ -77,7 +77,7 @@ static const std::vector<KernelChoice>& choices() {
         };
         for (auto& k : c)
             if (const TCKernels* t = tc_kernels(k.nu, k.W)) {   // one set of tensor-core kernels per (nu, width): the particle count is a run-time row mapping
-                k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve; k.solve_tc_lat = t->solve_lat;
+                k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve; k.solve_tc_lat = t->solve_lat; k.solve_tc_spec = t->solve_spec;
                 k.tc_bytes = t->bytes; k.tc_bytes_grad = t->bytes_grad; k.tc_bytes_solve = t->bytes_solve;
                 k.tc_tape_granules = t->tape_granules; k.tc_solve_tape_granules = t->solve_tape_granules; k.tc_cols = t->cols;
             }
@@ -102,6 +102,7 @@ struct sdempc_handle {
     float* d_tape_tc = nullptr; size_t tape_tc_bytes = 0;
     float* d_tcs_ws = nullptr; size_t tcs_ws_bytes = 0;   // per-CTA workspaces of the tensor-core solve
     int tcs_ppc_override = 0;                             // experiments: SDEMPC_TC_PPC
+    int tcs_spec = 1;                                     // SDEMPC_TC_SPEC=0: never the speculative build (tests compare the two)
     size_t smem_bytes_group = 0;
     size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
@@ -122,11 +123,11 @@ struct sdempc_handle {
     int sm_count = 0;
     int64_t launches = 0;
     int last_grid = 0;
-    int regs = 0, regs_tc = 0, regs_tc_lat = 0;
+    int regs = 0, regs_tc = 0, regs_tc_lat = 0, regs_tc_spec = 0;
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_tc = false, staged_tc_lat = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false;
     float last_ms = 0.f;
 };
 
@@ -215,7 +216,7 @@ struct TCSWsHost { size_t total; };
 static TCSWsHost tcs_ws_floats(int H, int NU, int RS, int TG) {
     const size_t n = (size_t)H * NU;
     TCSWsHost w;
-    w.total = 3 * n * RS + (size_t)SDEMPC_MAX_NU * RS + 16 * (size_t)RS + (size_t)(H + 1) * NX * RS + (size_t)H * 6 * 128 +
+    w.total = 3 * n * RS + (size_t)SDEMPC_MAX_NU * RS + 16 * (size_t)RS + (size_t)(H + 1) * NX * RS + (size_t)H * 6 * 128 + 16 * 128 +
               (size_t)H * TG * 128 * 4;
     return w;
 }
@@ -357,9 +358,11 @@ static int ensure_device(sdempc_handle* h) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.rollout_tc_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_grad));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
         cudaFuncAttributes ft;
         CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc)); h->regs_tc = ft.numRegs;
         CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc_lat)); h->regs_tc_lat = ft.numRegs;
+        CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc_spec)); h->regs_tc_spec = ft.numRegs;
         CUDA_TRY(cudaMalloc(&h->d_wimg_tc, h->wimg_tc.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_wimg_tc, h->wimg_tc.data(), h->wimg_tc.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -575,6 +578,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; k.tcs_sms = h->sm_count; }
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl;
     h->staged_tc = tcs; h->staged_tc_lat = tcs && tcs_lat;
+    h->staged_tc_spec = tcs && tcs_lat && h->tcs_spec && ppc * 8 <= 128 / P;   // (few problems per CTA: speculative gradient passes, mpc_tcsolve.cuh)
     return 0;
 }
 
@@ -597,7 +601,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
     }
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
-    const bool tcs = (fn == h->kc.solve_tc || fn == h->kc.solve_tc_lat) && fn != nullptr;
+    const bool tcs = (fn == h->kc.solve_tc || fn == h->kc.solve_tc_lat || fn == h->kc.solve_tc_spec) && fn != nullptr;
     const int threads = tcs ? 128 : spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     const size_t smem = tcs ? (size_t)h->kc.tc_bytes_solve : spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
     void* args[] = {const_cast<KParams*>(&k)};
@@ -607,7 +611,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
 }
 
 static void (*staged_kernel(const sdempc_handle* h))(KParams) {
-    return h->staged_tc ? (h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
+    return h->staged_tc ? (h->staged_tc_spec ? h->kc.solve_tc_spec : h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
            : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
@@ -669,6 +673,7 @@ int sdempc_create(const sdempc_config* cfg, const void* model_blob, size_t nbyte
     memcpy(h->weights.data(), (const char*)model_blob + sizeof mh, 2 * per_net * 4);
     pack_weights(h);
     if (h->kc.rollout_tc) pack_weights_tc(h);
+    if (const char* e = getenv("SDEMPC_TC_SPEC")) h->tcs_spec = atoi(e);
     if (const char* e = getenv("SDEMPC_TC_PPC")) h->tcs_ppc_override = atoi(e);   // experiments: problems per CTA of the tensor-core solve
     build_kparams(h);
     *out = h;
@@ -1025,7 +1030,7 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
     if (h->staged_tc) {
-        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
+        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_spec ? h->regs_tc_spec : h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
         return 0;
     }
     out[0] = (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;

@@ -20,14 +20,15 @@ __global__ void __launch_bounds__(128, 512 / TCLayout<NU, W>::COLS) mpc_tc_rollo
 
 // MINB = resident CTAs per SM the register budget is set for.  Two builds of the width-32 solve: 4 CTAs per SM (128 registers,
 // what tensor memory allows: large batches) and 2 CTAs per SM (164 registers, no spill: 11 % faster per CTA, used while the
-// batch needs at most two CTAs per SM).
-template <int NU, int W, int MINB>
+// batch needs at most two CTAs per SM).  SPECG: the build with the speculative gradient pass and per-problem phases
+// (mpc_tcsolve.cuh), for CTAs that own at most an eighth of their slots in problems.
+template <int NU, int W, int MINB, bool SPECG>
 __global__ void __launch_bounds__(128, MINB) mpc_tc_solve_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t tc_bars[2];
     __shared__ TCSShared sh;
-    tc_solve_body<NU, W>(P, tc_smem, &tmem_slot, tc_bars, sh);
+    tc_solve_body<NU, W, SPECG>(P, tc_smem, &tmem_slot, tc_bars, sh);
 }
 
 template <int NU, int W>
@@ -36,8 +37,9 @@ static TCKernels make_tc() {
     TCKernels k;
     k.rollout = mpc_tc_rollout_kernel<NU, W, false>;
     k.rollout_grad = mpc_tc_rollout_kernel<NU, W, true>;
-    k.solve = mpc_tc_solve_kernel<NU, W, 512 / L::COLS>;
-    k.solve_lat = (512 / L::COLS > 2) ? mpc_tc_solve_kernel<NU, W, 2> : k.solve;
+    k.solve = mpc_tc_solve_kernel<NU, W, 512 / L::COLS, false>;
+    k.solve_lat = (512 / L::COLS > 2) ? mpc_tc_solve_kernel<NU, W, 2, false> : k.solve;
+    k.solve_spec = mpc_tc_solve_kernel<NU, W, 2, true>;
     // Residency must be bounded by tensor memory (512 / COLS CTAs per SM), never exceed it: a CTA that the block
     // scheduler places beyond that spins in tcgen05.alloc while holding its slot (width 64, forward variant:
     // registers and shared memory allowed three CTAs, tensor memory two -- launches were bimodal, 0.30 / 0.41 ms).

@@ -404,6 +404,42 @@ def test_tensor_core_solve_teacher_forced_and_free_running(solver, O, vehicle, p
     assert abs(it_[:, 0].mean() - io[:, 0].mean()) <= 0.05 * io[:, 0].mean(), "same line-search effort"
 
 
+def test_tensor_core_solve_speculative_build_returns_the_same_bits(solver, monkeypatch):
+    """The build with the speculative gradient pass and per-problem phases (few problems per CTA, mpc_tcsolve.cuh) evaluates
+    the same expressions on the same operands as the plain build: plans, trajectories, telemetry and the whole decision
+    trace are identical bit for bit — over batch sizes from one problem per CTA up to an eighth of the slots, particles,
+    width 64, early stopping (problems leaving at different iterations) and warm-started ticks."""
+    cases = [("iris", 1, 40, {}), ("iris", 1, 12, dict(rtol=1e-3, atol=1e-3)), ("hexa", 1, 25, {}), ("hexa", 8, 20, {}), ("iris", 4, 20, {})]
+    for veh, Pn, iters, extra in cases:
+        cfg, blob, _ = make_setup(veh, "traj", tensor=True, max_iter=iters, num_particles=Pn, **extra)
+        tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.0, duration=20.0))
+        for B in (3, 148 + 5, 148 * (16 // Pn)):
+            x = random_states(B, B + Pn)
+            ct = np.linspace(0, 3, B).astype(np.float32)
+            rng = np.array([[5, b] for b in range(B)], np.uint64)
+            out = {}
+            for spec in ("1", "0"):
+                monkeypatch.setenv("SDEMPC_TC_SPEC", spec)
+                s = solver.MPCSolver(cfg, blob)
+                s.set_trajectory(tab)
+                up, ip = s.reset(B)
+                res = []
+                for tick in range(2):
+                    up, xe, ip, tr = s.solve(x, up, ip, curr_t=ct + 0.05 * tick, rng=rng, want_trace=True)
+                    res.append((up.copy(), xe.copy(), ip.copy(), tr.copy()))
+                out[spec] = (res, s.kernel_info())
+                s.close()
+            k1, k0 = out["1"][1], out["0"][1]
+            assert k1["problems_per_cta"] == k0["problems_per_cta"] and k1["ctas"] == k0["ctas"]
+            assert k1["regs_per_thread"] != k0["regs_per_thread"], "two different builds ran"
+            for tick, (a, b) in enumerate(zip(out["1"][0], out["0"][0])):
+                for name, va, vb in zip(("u_plan", "x_evol", "info", "trace"), a, b):
+                    if name == "info":
+                        va, vb = va[:, :7], vb[:, :7]          # (the last column is the measured solve time)
+                    ne = va.view(np.uint32) != vb.view(np.uint32)
+                    assert not ne.any(), (veh, Pn, B, tick, name, int(ne.sum()), np.argwhere(ne)[:4].tolist(), va[ne][:4], vb[ne][:4])
+
+
 def test_tensor_core_solve_modes_and_batches(solver, O):
     """The tensor-core solve through every reference selection of m_mpc (trajectory time, set-point, explicit window),
     warm-started over ticks, with early stopping, and at batch sizes that exercise one problem per CTA, the one-pass
