@@ -17,6 +17,11 @@ constexpr int GROUP_GW = 8;   // warps per CTA of the throughput kernel
 constexpr int group_gp(int nu, int w) { return (w == 32 && nu <= 4) ? 4 : (w == 32) ? 3 : 2; }
 constexpr int SPEC_LSW = 4;   // line-search warps of the latency kernel: one per SM sub-partition
 constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0/1/2 accepted, step rejected)
+// P > 1 latency kernel (mpc_pcluster.cuh): line-search and speculative-gradient REPLICAS of P warps each; at most 32 warps
+// = 8 CTAs (the portable cluster size) per problem
+constexpr int pc_lsw(int P) { return P >= 8 ? 2 : 4; }
+constexpr int pc_sgw(int P) { return P >= 8 ? 2 : 4; }
+constexpr int pc_cluster_ctas(int P) { return P * (pc_lsw(P) + pc_sgw(P)) / 4; }
 
 struct KernelChoice {
     void (*solve)(KParams);
@@ -26,7 +31,7 @@ struct KernelChoice {
     void (*closed_spec)(KParams);
     void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
     void (*closed_cl)(KParams);
-    void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of P*SPEC_LSW/4 CTAs
+    void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of pc_cluster_ctas(P) CTAs
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
@@ -327,11 +332,11 @@ __global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) 
     if constexpr (CL) cooperative_groups::this_cluster().sync();   // keep shared memory alive for the sibling CTA
 }
 
-// Latency kernel for P > 1 (mpc_pcluster.cuh): one problem per cluster of PP*LSW/4 CTAs, 4 warps per CTA.
-template <int NU, int W, int PP, int LSW>
+// Latency kernel for P > 1 (mpc_pcluster.cuh): one problem per cluster of PP*(LSW+SGW)/4 CTAs, 4 warps per CTA.
+template <int NU, int W, int PP, int LSW, int SGW>
 __global__ void __launch_bounds__(128, 1) mpc_pcluster_kernel(const __grid_constant__ KParams P) {
     using L = Layout<NU, W>;
-    using PC = PCluster<PP, LSW>;
+    using PC = PCluster<PP, LSW, SGW>;
     extern __shared__ __align__(128) float smem[];
     float* ws = smem;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::SMEM_FLOATS);
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(128, 1) mpc_pcluster_kernel(const __grid_const
         float s = P.info[b].stepsize;
         s = s > 0.f ? s : P.init_step;
         sdempc_info inf;
-        apg_solve_pcluster<NU, W, PP, LSW>(P, c, pc, warp, x0, s, inf,
+        apg_solve_pcluster<NU, W, PP, LSW, SGW>(P, c, pc, warp, x0, s, inf,
                                            P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
         if (pc.gwi == 0) {
             for (int i = lane; i < n; i += 32) P.u_plan_out[(size_t)b * n + i] = c.xk[i];
@@ -560,7 +565,7 @@ KernelChoice make_choice() {
     k.solve_pc = nullptr;
     k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
-    if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, SPEC_LSW>;
+    if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP)>;
     k.gp = group_gp(NU, W);
     if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
     if constexpr (PP == 1) {

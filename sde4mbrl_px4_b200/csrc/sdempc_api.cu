@@ -389,11 +389,11 @@ static bool use_cluster(const sdempc_handle* h, int B) {
     return use_spec(h, B) && h->kc.solve_cl != nullptr && 2 * B <= h->sm_count && !(h->cfg.flags & SDEMPC_F_NO_CLUSTER);
 }
 
-// P > 1: particle cluster (P * SPEC_LSW / 4 SMs per problem)
+// P > 1: particle cluster (pc_cluster_ctas(P) SMs per problem: line-search + speculative-gradient replicas)
 static bool use_pcluster(const sdempc_handle* h, int B) {
     if (h->kc.solve_pc == nullptr || h->cfg.maxls < 1) return false;
     if (h->cfg.flags & (SDEMPC_F_SEQUENTIAL_LS | SDEMPC_F_NO_CLUSTER)) return false;
-    return B * (h->kc.P * SPEC_LSW / 4) <= h->sm_count;
+    return B * pc_cluster_ctas(h->kc.P) <= h->sm_count;
 }
 
 static bool use_group(const sdempc_handle* h, int B) {
@@ -542,7 +542,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     const bool cl = !tcs && use_cluster(h, B), pcl = !tcs && use_pcluster(h, B);
     bool tcs_lat = false;
     const int ppc = tcs ? tcs_problems_per_cta(h, B, &tcs_lat) : 0, rs = 128;   // TCS_RS (mpc_tcsolve.cuh)
-    const int grid = tcs ? (B + ppc - 1) / ppc : pcl ? B * (h->kc.P * SPEC_LSW / 4) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
+    const int grid = tcs ? (B + ppc - 1) / ppc : pcl ? B * pc_cluster_ctas(h->kc.P) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
     if (tcs) { if ((rc = ensure_tcs_ws(h, grid, rs))) return rc; }
     else if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
@@ -584,7 +584,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
     if (fn != nullptr && (fn == h->kc.solve_cl || fn == h->kc.closed_cl || fn == h->kc.solve_pc)) {   // one cluster per problem
-        const unsigned cs = (fn == h->kc.solve_pc) ? (unsigned)(h->kc.P * SPEC_LSW / 4) : 2u;
+        const unsigned cs = (fn == h->kc.solve_pc) ? (unsigned)pc_cluster_ctas(h->kc.P) : 2u;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(SPEC_LSW * 32);
