@@ -376,6 +376,8 @@ def main():
             "frac_of_occupied_sms_fp32_peak": ach / (pk["fp32_tflops"] * sms / int(ki1["sm_count"])),
             "cycles_per_step_evaluation_on_the_critical_path":
                 pc(dev_l, 50) * 1e-3 * pk["sm_max_mhz"] * 1e6 / (float(np.mean(it_l)) * 2 * c1.horizon),
+            "chain_note": "tick cycles / (iterations x 2H): an upper bound — an iteration whose outcome was not speculated "
+                          "(5-12 % of them) adds a line-search pass and a gradient pass to the chain",
             "kernel": ki1}
         if not args.no_cpu_baseline:   # the CPU statement of the same tick on one host core
             from oracle import oracle as O

@@ -22,6 +22,8 @@ constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0
 constexpr int pc_lsw(int P) { return P >= 8 ? 2 : 4; }
 constexpr int pc_sgw(int P) { return P >= 8 ? 2 : 4; }
 constexpr int pc_cluster_ctas(int P) { return P * (pc_lsw(P) + pc_sgw(P)) / 4; }
+// P = 8 on a 16-CTA cluster (non-portable size, one per GPC): 4 + 4 replicas, candidates trial 0 / 1 / 2 accepted and rejected
+constexpr int PC16_LSW = 4, PC16_SGW = 4;
 
 struct KernelChoice {
     void (*solve)(KParams);
@@ -32,6 +34,7 @@ struct KernelChoice {
     void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
     void (*closed_cl)(KParams);
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of pc_cluster_ctas(P) CTAs
+    void (*solve_pc16)(KParams);   // P = 8: the same on a 16-CTA cluster with 4 + 4 replicas (nullptr otherwise)
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
@@ -562,10 +565,11 @@ KernelChoice make_choice() {
     k.closed_spec = nullptr;
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
-    k.solve_pc = nullptr;
+    k.solve_pc = k.solve_pc16 = nullptr;
     k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP)>;
+    if constexpr (PP == 8) k.solve_pc16 = mpc_pcluster_kernel<NU, W, PP, PC16_LSW, PC16_SGW>;
     k.gp = group_gp(NU, W);
     if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
     if constexpr (PP == 1) {

@@ -1,7 +1,7 @@
 // mpc_pcluster.cuh — latency kernel for P > 1 particles: one problem per thread-block cluster.
 //
 // The P particle rollouts of a problem are independent given the control sequence, and so are the line-search
-// trials of an iteration.  A cluster of P*(LSW+SGW)/4 CTAs (4 warps each, one per SM sub-partition, so that no two
+// trials of an iteration.  A cluster of P*(LSW+SGW)/4 CTAs (8 = the portable size, or 16 where the device takes it; 4 warps each, one per SM sub-partition, so that no two
 // warps share an issue port) holds LSW + SGW replicas x P particles of ONE problem: warp (l, p) integrates particle p.
 // Replicas l < LSW evaluate line-search trial base + l.  Replicas l >= LSW are SPECULATIVE-GRADIENT replicas (as in
 // apg_solve_latency for P = 1): while the trials run, replica LSW + c computes value_and_grad at the next extrapolation
@@ -23,8 +23,8 @@ namespace sdempc {
 
 template <int PP, int LSW, int SGW>
 struct PCluster {
-    static constexpr int TW = PP * (LSW + SGW);   // warps of the team (<= 32: one exchange value per lane)
-    static_assert(TW <= 32 && TW % 4 == 0, "team of at most 32 warps, whole CTAs");
+    static constexpr int TW = PP * (LSW + SGW);   // warps of the team (<= 64: two exchange values per lane)
+    static_assert(TW <= 64 && TW % 4 == 0 && 32 % PP == 0, "team of at most 64 warps, whole CTAs, replicas inside a half");
     static constexpr int CS = TW / 4;     // CTAs of the cluster
     int l, p, gwi;                        // replica, particle, warp index in the team
     float* xc_local;                      // this CTA's exchange area: [2 parities][4 warps][2 floats]
@@ -44,26 +44,38 @@ struct PCluster {
     }
 };
 
-// publish (a, b) of this warp, barrier, return every team warp's pair: lane w (< TW) holds warp w's pair
+// publish (a, b) of this warp, barrier, return every team warp's pair: lane w holds warp w's pair in (.x, .y) and warp
+// (w + 32)'s in (.z, .w)
 template <int PP, int LSW, int SGW>
-__device__ __forceinline__ float2 pc_exchange(const PCluster<PP, LSW, SGW>& pc, int lane, int warp_in_cta, int parity, float a, float b) {
+__device__ __forceinline__ float4 pc_exchange(const PCluster<PP, LSW, SGW>& pc, int lane, int warp_in_cta, int parity, float a, float b) {
+    constexpr int TW = PCluster<PP, LSW, SGW>::TW;
     if (lane == 0) {
         float* s = pc.xc_local + (parity * 4 + warp_in_cta) * 2;
         s[0] = a; s[1] = b;
     }
     pc.barrier();
-    float2 v = make_float2(0.f, 0.f);
-    if (lane < PCluster<PP, LSW, SGW>::TW) { const float* s = pc.slot(lane, parity); v.x = s[0]; v.y = s[1]; }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < TW) { const float* s = pc.slot(lane, parity); v.x = s[0]; v.y = s[1]; }
+    if (TW > 32 && lane + 32 < TW) { const float* s = pc.slot(lane + 32, parity); v.z = s[0]; v.w = s[1]; }
     return v;
 }
 
-// mean over the particles of replica r of the .x components (sequential sum in particle order, times 1/P)
+// mean over the particles of replica r of the first components (sequential sum in particle order, times 1/P); the PP
+// warps of a replica never straddle the two halves of the exchange (PP divides 32)
 template <int PP>
-__device__ __forceinline__ float pc_replica_mean(float vx, int r, float invP) {
-    float acc = __shfl_sync(0xffffffffu, vx, r * PP);
+__device__ __forceinline__ float pc_replica_mean(const float4& v, int r, float invP) {
+    const int w0 = r * PP, l0 = w0 & 31;
+    const float src = w0 < 32 ? v.x : v.z;
+    float acc = __shfl_sync(0xffffffffu, src, l0);
 #pragma unroll
-    for (int q = 1; q < PP; ++q) acc = acc + __shfl_sync(0xffffffffu, vx, r * PP + q);
+    for (int q = 1; q < PP; ++q) acc = acc + __shfl_sync(0xffffffffu, src, l0 + q);
     return acc * invP;
+}
+// second component published by the first warp of replica r
+template <int PP>
+__device__ __forceinline__ float pc_replica_second(const float4& v, int r) {
+    const int w0 = r * PP;
+    return __shfl_sync(0xffffffffu, w0 < 32 ? v.y : v.w, w0 & 31);
 }
 
 template <int NU, int W, int PP, int LSW, int SGW>
@@ -100,9 +112,9 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
             const float Jw = rollout_fwd<NU, W, 1>(P, c, c.yk, x0);
             rollout_bwd<NU, W>(P, c, c.yk);
             c.g = gsave;
-            const float2 v = pc_exchange<PP, LSW, SGW>(pc, lane, warp_in_cta, xpar, Jw, 0.f);
+            const float4 v = pc_exchange<PP, LSW, SGW>(pc, lane, warp_in_cta, xpar, Jw, 0.f);
             xpar ^= 1;
-            fy = pc_replica_mean<PP>(v.x, l, invP);
+            fy = pc_replica_mean<PP>(v, l, invP);
             mean_grad(l);
             if (it == 1) { Jx = fy; init_cost = fy; }
             if (SGW > 0) pc.barrier();   // a speculation warp overwrites its g2 next; its replica's other warps may still be reading it
@@ -165,17 +177,17 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
                 rollout_bwd<NU, W>(P, c, c.xp);
                 c.g = gsave;
             }
-            const float2 v = pc_exchange<PP, LSW, SGW>(pc, lane, warp_in_cta, xpar, Jw, dec);
+            const float4 v = pc_exchange<PP, LSW, SGW>(pc, lane, warp_in_cta, xpar, Jw, dec);
             xpar ^= 1;
             if (round == 0) {
 #pragma unroll
-                for (int cc = 0; cc < SGW; ++cc) fc[cc] = pc_replica_mean<PP>(v.x, LSW + cc, invP);
+                for (int cc = 0; cc < SGW; ++cc) fc[cc] = pc_replica_mean<PP>(v, LSW + cc, invP);
             }
             int q = 0;
             float Jq = 0.f;
             for (; q < LSW && base + q <= P.maxls; ++q) {
-                Jq = pc_replica_mean<PP>(v.x, q, invP);
-                const float dq = __shfl_sync(0xffffffffu, v.y, q * PP);
+                Jq = pc_replica_mean<PP>(v, q, invP);
+                const float dq = pc_replica_second<PP>(v, q);
                 if (Jq <= fma_(P.coef, dq, fy)) { ok = true; break; }
             }
             if (ok) { jsel = base + q; Jp = Jq; break; }
