@@ -22,8 +22,9 @@ constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0
 constexpr int pc_lsw(int P) { return P >= 8 ? 2 : 4; }
 constexpr int pc_sgw(int P) { return P >= 8 ? 2 : 4; }
 constexpr int pc_cluster_ctas(int P) { return P * (pc_lsw(P) + pc_sgw(P)) / 4; }
-// P = 8 on a 16-CTA cluster (non-portable size, one per GPC): 4 + 4 replicas, candidates trial 0 / 1 / 2 accepted and rejected
-constexpr int PC16_LSW = 4, PC16_SGW = 4;
+// P = 8, width 64 on a 16-CTA cluster (non-portable size) of TWO warps per CTA: the same 2 + 2 replicas spread over twice
+// the SMs, because four width-64 warps saturate an SM's shared-memory pipe (the weights are read from it every step)
+constexpr int PC16_WPC = 2;
 
 struct KernelChoice {
     void (*solve)(KParams);
@@ -34,7 +35,7 @@ struct KernelChoice {
     void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
     void (*closed_cl)(KParams);
     void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of pc_cluster_ctas(P) CTAs
-    void (*solve_pc16)(KParams);   // P = 8: the same on a 16-CTA cluster with 4 + 4 replicas (nullptr otherwise)
+    void (*solve_pc16)(KParams);   // P = 8, width 64: the same on a 16-CTA cluster of PC16_WPC warps per CTA (nullptr otherwise)
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
@@ -335,11 +336,11 @@ __global__ void __launch_bounds__(CL ? LSW * 32 : G * PP * (LSW + SGW) * 32, 1) 
     if constexpr (CL) cooperative_groups::this_cluster().sync();   // keep shared memory alive for the sibling CTA
 }
 
-// Latency kernel for P > 1 (mpc_pcluster.cuh): one problem per cluster of PP*(LSW+SGW)/4 CTAs, 4 warps per CTA.
-template <int NU, int W, int PP, int LSW, int SGW>
-__global__ void __launch_bounds__(128, 1) mpc_pcluster_kernel(const __grid_constant__ KParams P) {
+// Latency kernel for P > 1 (mpc_pcluster.cuh): one problem per cluster of PP*(LSW+SGW)/WPC CTAs, WPC warps per CTA.
+template <int NU, int W, int PP, int LSW, int SGW, int WPC = 4>
+__global__ void __launch_bounds__(WPC * 32, 1) mpc_pcluster_kernel(const __grid_constant__ KParams P) {
     using L = Layout<NU, W>;
-    using PC = PCluster<PP, LSW, SGW>;
+    using PC = PCluster<PP, LSW, SGW, WPC>;
     extern __shared__ __align__(128) float smem[];
     float* ws = smem;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::SMEM_FLOATS);
@@ -358,12 +359,12 @@ __global__ void __launch_bounds__(128, 1) mpc_pcluster_kernel(const __grid_const
     c.xk = wb + P.o_xk; c.yk = wb + P.o_yk; c.g = wb + P.o_g; c.g2 = wb + P.o_g2; c.xp = wb + P.o_xp; c.uprev = wb + P.o_uprev;
     c.xref = wb + P.o_xref; c.xi = wb + P.o_xi; c.xtape = wb + P.o_xtape; c.stape = wb + P.o_stape;
     c.bufA = wb + P.o_bufA; c.bufB = wb + P.o_bufB; c.act3 = wb + P.o_act3; c.lz = wb + P.o_lz; c.red = wb + P.o_red;
-    if (P.mtape_g != nullptr) c.mtape = P.mtape_g + ((size_t)blockIdx.x * 4 + warp) * (size_t)P.H * 2 * W;
+    if (P.mtape_g != nullptr) c.mtape = P.mtape_g + ((size_t)blockIdx.x * WPC + warp) * (size_t)P.H * 2 * W;
     else c.mtape = reinterpret_cast<float2*>(wb + P.o_mtape);
     c.load_regs(P.wimg);
 
     PC pc;
-    pc.gwi = crank * 4 + warp;
+    pc.gwi = crank * WPC + warp;
     pc.l = pc.gwi / PP;
     pc.p = pc.gwi % PP;
     pc.xc_local = team_base;
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(128, 1) mpc_pcluster_kernel(const __grid_const
         float s = P.info[b].stepsize;
         s = s > 0.f ? s : P.init_step;
         sdempc_info inf;
-        apg_solve_pcluster<NU, W, PP, LSW, SGW>(P, c, pc, warp, x0, s, inf,
+        apg_solve_pcluster<NU, W, PP, LSW, SGW, WPC>(P, c, pc, warp, x0, s, inf,
                                            P.trace ? P.trace + (size_t)b * P.max_iter * SDEMPC_TRACE_W : nullptr);
         if (pc.gwi == 0) {
             for (int i = lane; i < n; i += 32) P.u_plan_out[(size_t)b * n + i] = c.xk[i];
@@ -569,7 +570,7 @@ KernelChoice make_choice() {
     k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP)>;
-    if constexpr (PP == 8) k.solve_pc16 = mpc_pcluster_kernel<NU, W, PP, PC16_LSW, PC16_SGW>;
+    if constexpr (PP == 8 && W == 64) k.solve_pc16 = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP), PC16_WPC>;
     k.gp = group_gp(NU, W);
     if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
     if constexpr (PP == 1) {

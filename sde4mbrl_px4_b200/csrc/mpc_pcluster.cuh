@@ -1,8 +1,9 @@
 // mpc_pcluster.cuh — latency kernel for P > 1 particles: one problem per thread-block cluster.
 //
 // The P particle rollouts of a problem are independent given the control sequence, and so are the line-search
-// trials of an iteration.  A cluster of P*(LSW+SGW)/4 CTAs (8 = the portable size, or 16 where the device takes it; 4 warps each, one per SM sub-partition, so that no two
-// warps share an issue port) holds LSW + SGW replicas x P particles of ONE problem: warp (l, p) integrates particle p.
+// trials of an iteration.  A cluster of P*(LSW+SGW)/WPC CTAs (8 = the portable size, or 16 where the device takes it; WPC = 4 warps
+// each, one per SM sub-partition, so that no two warps share an issue port — or WPC = 2 for width 64, whose weights are
+// read from shared memory every step: four warps keep an SM's shared-memory pipe 69 % busy and wait on it) holds LSW + SGW replicas x P particles of ONE problem: warp (l, p) integrates particle p.
 // Replicas l < LSW evaluate line-search trial base + l.  Replicas l >= LSW are SPECULATIVE-GRADIENT replicas (as in
 // apg_solve_latency for P = 1): while the trials run, replica LSW + c computes value_and_grad at the next extrapolation
 // point for one possible outcome of the search — an accepted trial (SGW = 4: trials 0, 1, 2; SGW = 2: trial 1, the
@@ -21,13 +22,13 @@
 
 namespace sdempc {
 
-template <int PP, int LSW, int SGW>
+template <int PP, int LSW, int SGW, int WPC = 4>
 struct PCluster {
     static constexpr int TW = PP * (LSW + SGW);   // warps of the team (<= 64: two exchange values per lane)
-    static_assert(TW <= 64 && TW % 4 == 0 && 32 % PP == 0, "team of at most 64 warps, whole CTAs, replicas inside a half");
-    static constexpr int CS = TW / 4;     // CTAs of the cluster
+    static_assert(TW <= 64 && TW % WPC == 0 && 32 % PP == 0, "team of at most 64 warps, whole CTAs, replicas inside a half");
+    static constexpr int CS = TW / WPC;   // CTAs of the cluster
     int l, p, gwi;                        // replica, particle, warp index in the team
-    float* xc_local;                      // this CTA's exchange area: [2 parities][4 warps][2 floats]
+    float* xc_local;                      // this CTA's exchange area: [2 parities][WPC warps][2 floats]
     float* warp_base_local;               // this CTA's per-warp regions
     int ws_stride;
     __device__ __forceinline__ void barrier() const {
@@ -35,22 +36,22 @@ struct PCluster {
     }
     // exchange slot / region of team warp `w` (possibly in another CTA of the cluster)
     __device__ __forceinline__ const float* slot(int w, int parity) const {
-        const float* loc = xc_local + (parity * 4 + (w & 3)) * 2;
-        return cooperative_groups::this_cluster().map_shared_rank(loc, w >> 2);
+        const float* loc = xc_local + (parity * WPC + (w % WPC)) * 2;
+        return cooperative_groups::this_cluster().map_shared_rank(loc, w / WPC);
     }
     __device__ __forceinline__ const float* region(int w) const {
-        const float* loc = warp_base_local + (size_t)(w & 3) * ws_stride;
-        return cooperative_groups::this_cluster().map_shared_rank(loc, w >> 2);
+        const float* loc = warp_base_local + (size_t)(w % WPC) * ws_stride;
+        return cooperative_groups::this_cluster().map_shared_rank(loc, w / WPC);
     }
 };
 
 // publish (a, b) of this warp, barrier, return every team warp's pair: lane w holds warp w's pair in (.x, .y) and warp
 // (w + 32)'s in (.z, .w)
-template <int PP, int LSW, int SGW>
-__device__ __forceinline__ float4 pc_exchange(const PCluster<PP, LSW, SGW>& pc, int lane, int warp_in_cta, int parity, float a, float b) {
-    constexpr int TW = PCluster<PP, LSW, SGW>::TW;
+template <int PP, int LSW, int SGW, int WPC>
+__device__ __forceinline__ float4 pc_exchange(const PCluster<PP, LSW, SGW, WPC>& pc, int lane, int warp_in_cta, int parity, float a, float b) {
+    constexpr int TW = PCluster<PP, LSW, SGW, WPC>::TW;
     if (lane == 0) {
-        float* s = pc.xc_local + (parity * 4 + warp_in_cta) * 2;
+        float* s = pc.xc_local + (parity * WPC + warp_in_cta) * 2;
         s[0] = a; s[1] = b;
     }
     pc.barrier();
@@ -78,8 +79,8 @@ __device__ __forceinline__ float pc_replica_second(const float4& v, int r) {
     return __shfl_sync(0xffffffffu, w0 < 32 ? v.y : v.w, w0 & 31);
 }
 
-template <int NU, int W, int PP, int LSW, int SGW>
-__device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>& c, const PCluster<PP, LSW, SGW>& pc, int warp_in_cta,
+template <int NU, int W, int PP, int LSW, int SGW, int WPC>
+__device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>& c, const PCluster<PP, LSW, SGW, WPC>& pc, int warp_in_cta,
                                                    const float (&x0)[NX], float s, sdempc_info& inf, float* trace) {
     const int lane = c.lane;
     const int n = P.H * NU;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
             const float Jw = rollout_fwd<NU, W, 1>(P, c, c.yk, x0);
             rollout_bwd<NU, W>(P, c, c.yk);
             c.g = gsave;
-            const float4 v = pc_exchange<PP, LSW, SGW>(pc, lane, warp_in_cta, xpar, Jw, 0.f);
+            const float4 v = pc_exchange<PP, LSW, SGW, WPC>(pc, lane, warp_in_cta, xpar, Jw, 0.f);
             xpar ^= 1;
             fy = pc_replica_mean<PP>(v, l, invP);
             mean_grad(l);
@@ -177,7 +178,7 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
                 rollout_bwd<NU, W>(P, c, c.xp);
                 c.g = gsave;
             }
-            const float4 v = pc_exchange<PP, LSW, SGW>(pc, lane, warp_in_cta, xpar, Jw, dec);
+            const float4 v = pc_exchange<PP, LSW, SGW, WPC>(pc, lane, warp_in_cta, xpar, Jw, dec);
             xpar ^= 1;
             if (round == 0) {
 #pragma unroll

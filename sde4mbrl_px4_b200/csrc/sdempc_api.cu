@@ -356,7 +356,7 @@ static int ensure_device(sdempc_handle* h) {
                   cudaFuncSetAttribute(h->kc.solve_pc16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
         if (ok) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(16); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = h->smem_bytes_cl;
+            cfg.gridDim = dim3(16); cfg.blockDim = dim3(PC16_WPC * 32); cfg.dynamicSmemBytes = h->smem_bytes_cl;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -413,7 +413,7 @@ static bool use_pcluster(const sdempc_handle* h, int B) {
     if (h->cfg.flags & (SDEMPC_F_SEQUENTIAL_LS | SDEMPC_F_NO_CLUSTER)) return false;
     return B * pc_cluster_ctas(h->kc.P) <= h->sm_count;
 }
-// ... on 16-CTA clusters (P = 8, 4 + 4 replicas) while the device holds all of the batch's clusters at once
+// ... on 16-CTA clusters of two warps per CTA (P = 8, width 64) while the device holds all of the batch's clusters at once
 static bool use_pcluster16(const sdempc_handle* h, int B) {
     return use_pcluster(h, B) && h->kc.solve_pc16 != nullptr && B <= h->pc16_clusters;
 }
@@ -609,7 +609,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
         const unsigned cs = (fn == h->kc.solve_pc16) ? 16u : (fn == h->kc.solve_pc) ? (unsigned)pc_cluster_ctas(h->kc.P) : 2u;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(SPEC_LSW * 32);
+        cfg.blockDim = dim3((fn == h->kc.solve_pc16 ? PC16_WPC : SPEC_LSW) * 32);
         cfg.dynamicSmemBytes = h->smem_bytes_cl;
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
@@ -1055,7 +1055,7 @@ int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
         out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_spec ? h->regs_tc_spec : h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
         return 0;
     }
-    out[0] = (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    out[0] = h->staged_pc16 ? PC16_WPC * 32 : (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
     out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * h->kc.gp : h->kc.G;
     out[3] = h->regs;
