@@ -17,14 +17,15 @@ constexpr int GROUP_GW = 8;   // warps per CTA of the throughput kernel
 constexpr int group_gp(int nu, int w) { return (w == 32 && nu <= 4) ? 4 : (w == 32) ? 3 : 2; }
 constexpr int SPEC_LSW = 4;   // line-search warps of the latency kernel: one per SM sub-partition
 constexpr int SPEC_SGW = 4;   // speculative-gradient warps (candidates: trial 0/1/2 accepted, step rejected)
-// P > 1 latency kernel (mpc_pcluster.cuh): line-search and speculative-gradient REPLICAS of P warps each; at most 32 warps
-// = 8 CTAs (the portable cluster size) per problem
+// Cluster latency kernel (mpc_pcluster.cuh): line-search and speculative-gradient REPLICAS of P warps each, at most 32 warps
+// per problem.  Two shapes: "compact" = 4 warps per CTA (one per SM sub-partition; P = 8: 8 CTAs, the portable cluster
+// size) and "wide" = the same warps at 2 per CTA on twice the SMs — the warps of an SM share its shared-memory pipe, which
+// four width-64 warps saturate (weights read from shared memory every step) and four width-32 warps load enough to cost 6 %.
 constexpr int pc_lsw(int P) { return P >= 8 ? 2 : 4; }
 constexpr int pc_sgw(int P) { return P >= 8 ? 2 : 4; }
-constexpr int pc_cluster_ctas(int P) { return P * (pc_lsw(P) + pc_sgw(P)) / 4; }
-// P = 8, width 64 on a 16-CTA cluster (non-portable size) of TWO warps per CTA: the same 2 + 2 replicas spread over twice
-// the SMs, because four width-64 warps saturate an SM's shared-memory pipe (the weights are read from it every step)
-constexpr int PC16_WPC = 2;
+constexpr int PC_WPC = 4;
+constexpr int pcw_wpc(int) { return 2; }   // warps per CTA of the wide shape (P = 1 on 8 CTAs of ONE warp: 6.40 ms against 6.03)
+constexpr int pc_cluster_ctas(int P, int wpc) { return P * (pc_lsw(P) + pc_sgw(P)) / wpc; }
 
 struct KernelChoice {
     void (*solve)(KParams);
@@ -34,8 +35,8 @@ struct KernelChoice {
     void (*closed_spec)(KParams);
     void (*solve_cl)(KParams);     // latency mode on a 2-CTA cluster (line search on one SM, speculation on its neighbour)
     void (*closed_cl)(KParams);
-    void (*solve_pc)(KParams);     // P > 1 latency mode: one problem per cluster of pc_cluster_ctas(P) CTAs
-    void (*solve_pc16)(KParams);   // P = 8, width 64: the same on a 16-CTA cluster of PC16_WPC warps per CTA (nullptr otherwise)
+    void (*solve_pc)(KParams);     // cluster latency kernel, compact shape: pc_cluster_ctas(P, PC_WPC) CTAs per problem
+    void (*solve_pcw)(KParams);    // ... wide shape: pc_cluster_ctas(P, pcw_wpc(P)) CTAs per problem (16 for P >= 4: non-portable size)
     void (*solve_group)(KParams);  // throughput mode: GROUP_GW warps x gp problems per CTA (P == 1)
     void (*rollout_tc)(KParams);   // tensor-core forward rollout (any power-of-two particle count), SDEMPC_F_TENSOR
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
@@ -566,11 +567,11 @@ KernelChoice make_choice() {
     k.closed_spec = nullptr;
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
-    k.solve_pc = k.solve_pc16 = nullptr;
+    k.solve_pc = k.solve_pcw = nullptr;
     k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
-    if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP)>;
-    if constexpr (PP == 8 && W == 64) k.solve_pc16 = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP), PC16_WPC>;
+    if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP), PC_WPC>;
+    if constexpr (PP == 1 || PP == 2 || PP == 4 || PP == 8) k.solve_pcw = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP), pcw_wpc(PP)>;
     k.gp = group_gp(NU, W);
     if constexpr (PP == 1) k.solve_group = mpc_group_kernel<NU, W, group_gp(NU, W), GROUP_GW>;
     if constexpr (PP == 1) {

@@ -124,11 +124,11 @@ struct sdempc_handle {
     int64_t launches = 0;
     int last_grid = 0;
     int regs = 0, regs_tc = 0, regs_tc_lat = 0, regs_tc_spec = 0;
-    int pc16_clusters = 0;                                // 16-CTA clusters of the P = 8 latency kernel the device holds at once
+    int pcw_clusters = 0;                                 // clusters of the wide shape of the cluster latency kernel the device holds at once
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_pc16 = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_pcw = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false;
     float last_ms = 0.f;
 };
 
@@ -350,22 +350,23 @@ static int ensure_device(sdempc_handle* h) {
     }
     if (h->kc.solve_pc)
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_pc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl));
-    if (h->kc.solve_pc16) {   // 16-CTA clusters are a non-portable size: ask the device how many it can hold at once (0: not at all)
-        h->pc16_clusters = 0;
-        bool ok = cudaFuncSetAttribute(h->kc.solve_pc16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl) == cudaSuccess &&
-                  cudaFuncSetAttribute(h->kc.solve_pc16, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (h->kc.solve_pcw) {   // wide cluster shape; 16 CTAs are a non-portable size: ask the device how many it holds at once (0: none)
+        const int cs = pc_cluster_ctas(h->kc.P, pcw_wpc(h->kc.P));
+        h->pcw_clusters = 0;
+        bool ok = cudaFuncSetAttribute(h->kc.solve_pcw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes_cl) == cudaSuccess;
+        if (ok && cs > 8) ok = cudaFuncSetAttribute(h->kc.solve_pcw, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
         if (ok) {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(16); cfg.blockDim = dim3(PC16_WPC * 32); cfg.dynamicSmemBytes = h->smem_bytes_cl;
+            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(pcw_wpc(h->kc.P) * 32); cfg.dynamicSmemBytes = h->smem_bytes_cl;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 16; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, h->kc.solve_pc16, &cfg) == cudaSuccess) h->pc16_clusters = nc;
+            if (cudaOccupancyMaxActiveClusters(&nc, h->kc.solve_pcw, &cfg) == cudaSuccess) h->pcw_clusters = nc;
         }
         (void)cudaGetLastError();
-        if (const char* e = getenv("SDEMPC_PC16")) { if (atoi(e) == 0) h->pc16_clusters = 0; }   // experiments: the portable cluster only
+        if (const char* e = getenv("SDEMPC_PCW")) { if (atoi(e) == 0) h->pcw_clusters = 0; }   // experiments: never the wide shape
     }
     if (h->kc.solve_group) {
         if (h->smem_bytes_group > (size_t)prop.sharedMemPerBlockOptin) h->kc.solve_group = nullptr;   // does not fit: use one warp per problem
@@ -407,15 +408,18 @@ static bool use_cluster(const sdempc_handle* h, int B) {
     return use_spec(h, B) && h->kc.solve_cl != nullptr && 2 * B <= h->sm_count && !(h->cfg.flags & SDEMPC_F_NO_CLUSTER);
 }
 
-// P > 1: particle cluster (pc_cluster_ctas(P) SMs per problem: line-search + speculative-gradient replicas)
+// cluster latency kernel (mpc_pcluster.cuh), compact shape: P > 1, the whole batch resident at once
 static bool use_pcluster(const sdempc_handle* h, int B) {
     if (h->kc.solve_pc == nullptr || h->cfg.maxls < 1) return false;
     if (h->cfg.flags & (SDEMPC_F_SEQUENTIAL_LS | SDEMPC_F_NO_CLUSTER)) return false;
-    return B * pc_cluster_ctas(h->kc.P) <= h->sm_count;
+    return B * pc_cluster_ctas(h->kc.P, PC_WPC) <= h->sm_count;
 }
-// ... on 16-CTA clusters of two warps per CTA (P = 8, width 64) while the device holds all of the batch's clusters at once
-static bool use_pcluster16(const sdempc_handle* h, int B) {
-    return use_pcluster(h, B) && h->kc.solve_pc16 != nullptr && B <= h->pc16_clusters;
+// ... wide shape (two warps per SM), while the device holds all of the batch's clusters at once
+static bool use_pcluster_wide(const sdempc_handle* h, int B) {
+    if (h->kc.solve_pcw == nullptr || h->cfg.maxls < 1 || B > h->pcw_clusters) return false;
+    if (h->cfg.flags & (SDEMPC_F_SEQUENTIAL_LS | SDEMPC_F_NO_CLUSTER)) return false;
+    if (h->kc.P == 1 && !use_spec(h, B)) return false;
+    return B * pc_cluster_ctas(h->kc.P, pcw_wpc(h->kc.P)) <= h->sm_count;
 }
 
 static bool use_group(const sdempc_handle* h, int B) {
@@ -559,12 +563,12 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     const bool tcs = (h->cfg.flags & SDEMPC_F_TENSOR) != 0;
     if (tcs && (!h->kc.solve_tc || P > 32 || (P & (P - 1)) != 0 || h->cfg.u_slew_constr_coeff != 0.0f))
         return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core solve supports 1, 2, 4, ... 32 particles and no input-rate constraint");
-    const bool spec = !tcs && use_spec(h, B), group = !tcs && use_group(h, B);
+    const bool pclw = !tcs && use_pcluster_wide(h, B), pcl = !tcs && (pclw || use_pcluster(h, B));
+    const bool spec = !tcs && !pcl && use_spec(h, B), group = !tcs && use_group(h, B), cl = !tcs && !pcl && use_cluster(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
-    const bool cl = !tcs && use_cluster(h, B), pcl = !tcs && use_pcluster(h, B), pcl16 = !tcs && use_pcluster16(h, B);
     bool tcs_lat = false;
     const int ppc = tcs ? tcs_problems_per_cta(h, B, &tcs_lat) : 0, rs = 128;   // TCS_RS (mpc_tcsolve.cuh)
-    const int grid = tcs ? (B + ppc - 1) / ppc : pcl16 ? B * 16 : pcl ? B * pc_cluster_ctas(h->kc.P) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
+    const int grid = tcs ? (B + ppc - 1) / ppc : pclw ? B * pc_cluster_ctas(h->kc.P, pcw_wpc(h->kc.P)) : pcl ? B * pc_cluster_ctas(h->kc.P, PC_WPC) : cl ? 2 * B : spec ? std::min(B, h->sm_count)
                           : group ? std::max(1, std::min((B + 2 * GROUP_GW - 1) / (2 * GROUP_GW), h->sm_count)) : grid_for(h, B);
     if (tcs) { if ((rc = ensure_tcs_ws(h, grid, rs))) return rc; }
     else if (group) { if ((rc = ensure_mtape_group(h, grid))) return rc; }
@@ -598,18 +602,18 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.trace = a->trace ? h->d_trace : nullptr;
     k.wimg = h->d_wimg; k.traj = h->d_traj; k.T = h->T; k.mtape_g = group ? h->d_mtape_group : h->d_mtape;
     if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; k.tcs_sms = h->sm_count; }
-    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl; h->staged_pc16 = pcl16;
+    h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl; h->staged_pcw = pclw;
     h->staged_tc = tcs; h->staged_tc_lat = tcs && tcs_lat;
     h->staged_tc_spec = tcs && tcs_lat && h->tcs_spec && ppc * 8 <= 128 / P;   // (few problems per CTA: speculative gradient passes, mpc_tcsolve.cuh)
     return 0;
 }
 
 static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int grid) {
-    if (fn != nullptr && (fn == h->kc.solve_cl || fn == h->kc.closed_cl || fn == h->kc.solve_pc || fn == h->kc.solve_pc16)) {   // one cluster per problem
-        const unsigned cs = (fn == h->kc.solve_pc16) ? 16u : (fn == h->kc.solve_pc) ? (unsigned)pc_cluster_ctas(h->kc.P) : 2u;
+    if (fn != nullptr && (fn == h->kc.solve_cl || fn == h->kc.closed_cl || fn == h->kc.solve_pc || fn == h->kc.solve_pcw)) {   // one cluster per problem
+        const unsigned cs = (fn == h->kc.solve_pcw) ? (unsigned)pc_cluster_ctas(h->kc.P, pcw_wpc(h->kc.P)) : (fn == h->kc.solve_pc) ? (unsigned)pc_cluster_ctas(h->kc.P, PC_WPC) : 2u;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3((fn == h->kc.solve_pc16 ? PC16_WPC : SPEC_LSW) * 32);
+        cfg.blockDim = dim3((fn == h->kc.solve_pcw ? pcw_wpc(h->kc.P) : SPEC_LSW) * 32);
         cfg.dynamicSmemBytes = h->smem_bytes_cl;
         cfg.stream = h->stream;
         cudaLaunchAttribute attr[1];
@@ -633,7 +637,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
 }
 
 static void (*staged_kernel(const sdempc_handle* h))(KParams) {
-    return h->staged_tc ? (h->staged_tc_spec ? h->kc.solve_tc_spec : h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pc16 ? h->kc.solve_pc16 : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
+    return h->staged_tc ? (h->staged_tc_spec ? h->kc.solve_tc_spec : h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pcw ? h->kc.solve_pcw : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
            : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
@@ -1055,7 +1059,7 @@ int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
         out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_spec ? h->regs_tc_spec : h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
         return 0;
     }
-    out[0] = h->staged_pc16 ? PC16_WPC * 32 : (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
+    out[0] = h->staged_pcw ? pcw_wpc(h->kc.P) * 32 : (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     out[1] = (int32_t)(h->staged_spec ? h->smem_bytes_spec : h->staged_group ? h->smem_bytes_group : h->smem_bytes);
     out[2] = (h->staged_spec || h->staged_pc) ? 1 : h->staged_group ? GROUP_GW * h->kc.gp : h->kc.G;
     out[3] = h->regs;

@@ -128,7 +128,7 @@ def test_free_running_solve(solver, O, vehicle, mode, P, iters):
 
 
 @pytest.mark.parametrize("vehicle,width", [("iris", None), ("hexa", None), ("hexa", 32)])
-def test_three_kernels_agree(solver, O, vehicle, width):
+def test_three_kernels_agree(solver, O, vehicle, width, monkeypatch):
     """The latency kernel (line-search trials evaluated concurrently on 4 sibling warps, one per SM sub-partition,
     default for B <= #SMs), the throughput kernel (4 problems per warp: rigid-body algebra with lane = problem,
     networks with lane = hidden unit; default for B > #SMs when P = 1 and width 32) and the one-warp-per-problem
@@ -145,16 +145,22 @@ def test_three_kernels_agree(solver, O, vehicle, width):
     i0[::3, 1] = 3e-6                     # mixed carried step sizes
     uo, xeo, infoo, tro = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
     assert len(set(infoo[:, 2])) > 1 or True
-    # (flags, batch, expected threads per CTA; 255 = 8-warp latency kernel, 128 = 2-CTA cluster latency kernel)
-    modes = [(dict(speculative_ls=True), B, 255), (dict(sequential_ls=True), B, 256), (dict(), 9, 128),
+    # (flags, batch, expected threads per CTA; 255 = 8-warp latency kernel, 128 = 2-CTA cluster latency kernel, 64 = the
+    # cluster latency kernel in its wide shape: 4 CTAs of two warps per problem; "nowide": SDEMPC_PCW=0)
+    modes = [(dict(speculative_ls=True), B, 255), (dict(sequential_ls=True), B, 256), (dict(), 9, 64), (dict(nowide=True), 9, 128),
              (dict(no_cluster=True), 9, 255), (dict(), B, 256)]
     modes.append((dict(group=True), 7, 256))
     for mode, n, threads in modes:
+        mode = dict(mode)
+        if mode.pop("nowide", False):
+            monkeypatch.setenv("SDEMPC_PCW", "0")
+        else:
+            monkeypatch.delenv("SDEMPC_PCW", raising=False)
         cfg, s, _ = _pair(solver, O, vehicle, "traj", **ov, **mode)
         u, xe, info, tr = s.solve(pr["x"][:n], u0[:n], i0[:n], xref_win=pr["xref_win"][:n], rng=pr["rng"][:n], want_trace=True)
         ki = s.kernel_info()
         assert ki["threads_per_cta"] == (256 if threads == 255 else threads), (mode, ki)
-        if threads in (255, 128):
+        if threads in (255, 128, 64):
             assert ki["problems_per_cta"] == 1, ki       # a latency kernel (4 line-search + 4 speculation warps)
         if mode == dict(group=True):   # the throughput kernel was used: 8 warps x (4 | 3 | 2) problems
             assert ki["problems_per_cta"] == {("iris", None): 32, ("hexa", None): 16, ("hexa", 32): 24}[(vehicle, width)], ki
@@ -166,27 +172,25 @@ def test_three_kernels_agree(solver, O, vehicle, width):
 def test_particle_cluster_kernel(solver, O, vehicle, P, monkeypatch):
     """P > 1 latency kernel (one problem per thread-block cluster: line-search and speculative-gradient replicas of P particle
     warps each, DSMEM exchange of the particle means, trial results and speculated gradients) against the team kernel
-    (P warps in one CTA) and the oracle.  Width 64 with 8 particles runs on a 16-CTA cluster of two warps per CTA where the
-    device holds one, on the portable 8-CTA cluster of four warps otherwise: both are checked."""
+    (P warps in one CTA) and the oracle, in both cluster shapes."""
     ov = dict(num_particles=P, max_iter=25)
     cfg, s, o = _pair(solver, O, vehicle, "traj", **ov)
     B = 3
     pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=40 + P)
     u0, i0 = s.reset(B)
     b = o.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
-    wide = vehicle == "hexa" and P == 8
-    runs = [(dict(), None, (64, 128) if wide else (128,)), (dict(sequential_ls=True), None, (256,))]
-    if wide:
-        runs.append((dict(), "0", (128,)))
-    for mode, pc16, threads in runs:
-        if pc16 is not None:
-            monkeypatch.setenv("SDEMPC_PC16", pc16)
+    # default: the wide shape (two warps per CTA; 16 CTAs for P >= 4, taken when the device holds such a cluster), with
+    # SDEMPC_PCW=0 the compact one (four warps per CTA); sequential_ls: the team kernel
+    runs = [(dict(), None, (64, 128)), (dict(sequential_ls=True), None, (256,)), (dict(), "0", (128,))]
+    for mode, pcw, threads in runs:
+        if pcw is not None:
+            monkeypatch.setenv("SDEMPC_PCW", pcw)
         _, sm, _ = _pair(solver, O, vehicle, "traj", **ov, **mode)
         a = sm.solve(pr["x"], u0, i0, xref_win=pr["xref_win"], rng=pr["rng"], want_trace=True)
         assert sm.kernel_info()["threads_per_cta"] in threads, sm.kernel_info()
         _eq(a[3], b[3], f"trace {mode}"); _eq(a[0], b[0], f"u* {mode}"); _eq(a[1], b[1], f"x_evol {mode}")
         _eq(a[2][:, :7], b[2][:, :7], f"telemetry {mode}")
-        monkeypatch.delenv("SDEMPC_PC16", raising=False)
+        monkeypatch.delenv("SDEMPC_PCW", raising=False)
 
 
 @pytest.mark.parametrize("mode", [{}, {"group": True}, {"sequential_ls": True}])
