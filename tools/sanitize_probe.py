@@ -5,7 +5,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sde4mbrl_px4_b200 import config, model_io, solver, synthetic, trajectory
-which = sys.argv[1:] or ["cluster", "spec8", "warp", "group", "pcluster", "team", "closed", "rollout", "hexa"]
+which = sys.argv[1:] or ["cluster", "spec8", "warp", "group", "pcluster", "pcluster8", "team", "closed", "rollout", "hexa", "tcs", "tcs_spec", "tcs_p8"]
 def run(name, vehicle="iris", B=3, P=1, iters=2, **flags):
     cfgd = config.load_yaml(os.path.join(ROOT, "configs", f"{vehicle}_traj.yaml"))
     cfg = config.build_config(cfgd, max_iter=iters, num_particles=P, **flags)
@@ -26,6 +26,10 @@ if "spec8" in which: run("spec8", no_cluster=True)
 if "warp" in which: run("warp", sequential_ls=True, B=9)
 if "group" in which: run("group", group=True, B=7)
 if "pcluster" in which: run("pcluster", P=2, B=2)
+if "pcluster8" in which: run("pcluster8", vehicle="hexa", P=8, B=1, iters=4)      # 16-CTA cluster of two warps per CTA
+if "tcs" in which: run("tcs", B=148 * 20, iters=3, tensor=True)                     # tensor-core solve, plain build (20 problems per CTA)
+if "tcs_spec" in which: run("tcs_spec", B=40, iters=4, tensor=True)                 # speculative build, one problem per CTA
+if "tcs_p8" in which: run("tcs_p8", vehicle="hexa", P=8, B=700, iters=2, tensor=True)   # 5 problems x 8 particles per CTA: plain build
 if "team" in which: run("team", P=2, B=3, sequential_ls=True)
 if "closed" in which: run("closed", B=2)
 if "rollout" in which: run("rollout", P=2, B=3)
