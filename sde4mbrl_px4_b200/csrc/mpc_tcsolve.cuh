@@ -89,7 +89,7 @@ __device__ __forceinline__ void softplus_sigmoid_fast(float s, float& sp, float&
 }  // namespace tc
 
 // Body of the solve kernel.  sB: weight image (TCLayout, forward + adjoint parts).  bars[0]: weight staging, bars[1]: MMA.
-// SPECG = true: the build for CTAs with few problems (PPC <= slots / 8), where most slots would idle.
+// SPECG = true: the build for CTAs with few problems (PPC <= slots / 4), where most slots would idle.
 //   (1) SPECULATIVE GRADIENT PASSES.  Next to the line-search trials the free slots run the forward pass of the NEXT gradient
 //       evaluation for the likely outcomes, recording a tape each: "R" at x_k, where a rejected step restarts from (30 % of
 //       the iterations of the benchmark problems end that way, and x_k is known before the search), and one per trial j at
@@ -103,10 +103,14 @@ __device__ __forceinline__ void softplus_sigmoid_fast(float s, float& sp, float&
 //   Problems are independent, every task evaluates the same expressions on the same operands as in the other build, and
 //   a tensor-memory lane's result does not depend on which lane it is: the two builds return identical bits
 //   (tests/test_gpu_parity.py::test_tensor_core_solve_speculative_build_returns_the_same_bits).
-//   Measured (iris, 200 iterations, one CTA per SM): 7 problems per CTA 35.8 -> 27.7 ms, 14 per CTA 34.1 -> 29 ms.  With 28
-//   per CTA (two trials + R + one speculation each) the passes themselves get 1.3x slower — four warps of rows with
-//   distinct operands instead of one, twice the tape — and the build loses (36.8 against 35.9 ms): hence PPC <= slots / 8.
-template <int NU, int W, bool SPECG>
+//   Measured (iris, 200 iterations, one CTA per SM): 7 problems per CTA 35.8 -> 25.0 ms, 14 per CTA 34.1 -> 25.5 ms, 28 per CTA
+//   (two trials + R + one speculation each) 34.6 -> 33.5 ms; width 64: 28 per CTA 59.4 -> 51.0 ms, 4 problems x 8 particles
+//   59.6 -> 49.8 ms.  (Before the forward pass loaded its operands a step ahead into registers — PFR below — the build LOST at
+//   28 per CTA, 36.8 against 35.9 ms: four warps of rows with distinct operands exposed an L1 / L2 round trip per step.)
+// PFR = true (the builds with the register budget of two CTAs per SM): the operands of step t + 1 (controls, gradient, x_k,
+// noise, reference row: 31-35 values per row) are loaded into registers at the top of step t — a full step ahead of their
+// use — instead of being prefetched towards L1 and loaded when needed (which still exposes an L1 / L2 round trip per step).
+template <int NU, int W, bool SPECG, bool PFR>
 __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* sB, uint32_t* tmem_base_slot, uint64_t* bars,
                                               TCSShared& sh) {
     using L = TCSLayout<NU, W>;
@@ -463,32 +467,54 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
         [[maybe_unused]] const float* xkq = XK + q;
         const float* xiq = XI + xi_row;
         const float* xrq = XREF + q;
-        for (int t = 0; t < P.H; ++t) {
+        // operands of one step of my row
+        float o_y[NU], o_g[NU], o_xk[NU], o_xi[6], o_xr[NX];
+        auto load_ops = [&](int t) {
             const float* yt = yq + t * (NU * RS);
             const float* gt = gq + t * (NU * RS);
             const float* xit = xiq + t * (6 * 128);
             const float* xrt = xrq + (t + 1) * (NX * RS);
 #pragma unroll
             for (int i = 0; i < NU; ++i) {
-                const float yv = yt[i * RS];
+                o_y[i] = yt[i * RS];
+                o_g[i] = (mode == 0) ? gt[i * RS] : 0.f;
+                if constexpr (SPECG) o_xk[i] = spec ? xkq[(t * NU + i) * RS] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) o_xi[i] = xit[i * 128];
+#pragma unroll
+            for (int i = 0; i < NX; ++i) o_xr[i] = xrt[i * RS];
+        };
+        if constexpr (PFR) load_ops(0);
+        for (int t = 0; t < P.H; ++t) {
+            if constexpr (!PFR) load_ops(t);
+            float xi[6], xr[NX];
+#pragma unroll
+            for (int i = 0; i < NU; ++i) {
+                const float yv = o_y[i];
                 if (mode == 0) {
-                    const float gv = gt[i * RS];
+                    const float gv = o_g[i];
                     const float xv = clipf(fma_(-s_t, gv, yv), P.u_lo[i], P.u_hi[i]);
                     dec = fma_(gv, xv - yv, dec);
                     u[i] = xv;
                     if constexpr (SPECG) {   // the y_{k+1} this trial gives if accepted: the expression of plan_update
-                        if (spec) u[i] = clipf(fma_(beta_t, xv - xkq[(t * NU + i) * RS], xv), P.u_lo[i], P.u_hi[i]);
+                        if (spec) u[i] = clipf(fma_(beta_t, xv - o_xk[i], xv), P.u_lo[i], P.u_hi[i]);
                     }
                 } else {
                     u[i] = yv;
                 }
             }
-            float xi[6], xr[NX];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) xi[i] = xit[i * 128];
+            for (int i = 0; i < 6; ++i) xi[i] = o_xi[i];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) xr[i] = xrt[i * RS];
-            if (lone_cta && t + 1 < P.H) {   // next step's operands towards L1 while this step's contractions run (CTA alone on its SM)
+            for (int i = 0; i < NX; ++i) xr[i] = o_xr[i];
+            if constexpr (PFR) {
+                if (t + 1 < P.H) load_ops(t + 1);   // in flight during this step's contractions
+            } else if (lone_cta && t + 1 < P.H) {   // next step's operands towards L1 while this step's contractions run (CTA alone on its SM)
+                const float* yt = yq + t * (NU * RS);
+                const float* gt = gq + t * (NU * RS);
+                const float* xit = xiq + t * (6 * 128);
+                const float* xrt = xrq + (t + 1) * (NX * RS);
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
                     tc::prefetch_l1(yt + (NU + i) * RS);
@@ -722,6 +748,8 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     for (int g = 0; g < L::STG; ++g) { if (lone_cta) tc::prefetch_l1(tp(t - 1, g)); else tc::prefetch_l2(tp(t - 1, g)); }
                 }
                 float xt[NX], xi[6], xr[NX];
+                // (loading these a step ahead into registers, as the forward pass does with its operands, LOSES here: 34.6 -> 36.8 ms
+                // at 4096 problems — 32 more live registers across three contraction waits)
                 const float4 s0 = ldt(t, L::S_ST), s1 = ldt(t, L::S_ST + 1), s2 = ldt(t, L::S_ST + 2), s3 = ldt(t, L::S_ST + 3),
                              s4 = ldt(t, L::S_ST + 4);
                 {

@@ -102,7 +102,7 @@ struct sdempc_handle {
     float* d_tape_tc = nullptr; size_t tape_tc_bytes = 0;
     float* d_tcs_ws = nullptr; size_t tcs_ws_bytes = 0;   // per-CTA workspaces of the tensor-core solve
     int tcs_ppc_override = 0;                             // experiments: SDEMPC_TC_PPC
-    int tcs_spec = 1;                                     // SDEMPC_TC_SPEC=0: never the speculative build (tests compare the two)
+    int tcs_spec = 1;                                     // SDEMPC_TC_SPEC=0: never the speculative build (tests compare the two); 2: only up to slots / 8
     size_t smem_bytes_group = 0;
     size_t smem_bytes = 0, smem_bytes_spec = 0, smem_bytes_cl = 0;
     // lazily created device state
@@ -604,7 +604,7 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; k.tcs_sms = h->sm_count; }
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl; h->staged_pcw = pclw;
     h->staged_tc = tcs; h->staged_tc_lat = tcs && tcs_lat;
-    h->staged_tc_spec = tcs && tcs_lat && h->tcs_spec && ppc * 8 <= 128 / P;   // (few problems per CTA: speculative gradient passes, mpc_tcsolve.cuh)
+    h->staged_tc_spec = tcs && tcs_lat && h->tcs_spec && ppc * (h->tcs_spec == 2 ? 8 : 4) <= 128 / P;   // (few problems per CTA: speculative gradient passes, mpc_tcsolve.cuh)
     return 0;
 }
 

@@ -21,14 +21,14 @@ __global__ void __launch_bounds__(128, 512 / TCLayout<NU, W>::COLS) mpc_tc_rollo
 // MINB = resident CTAs per SM the register budget is set for.  Two builds of the width-32 solve: 4 CTAs per SM (128 registers,
 // what tensor memory allows: large batches) and 2 CTAs per SM (164 registers, no spill: 11 % faster per CTA, used while the
 // batch needs at most two CTAs per SM).  SPECG: the build with the speculative gradient pass and per-problem phases
-// (mpc_tcsolve.cuh), for CTAs that own at most an eighth of their slots in problems.
+// (mpc_tcsolve.cuh), for CTAs that own at most a quarter of their slots in problems.
 template <int NU, int W, int MINB, bool SPECG>
 __global__ void __launch_bounds__(128, MINB) mpc_tc_solve_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t tc_bars[2];
     __shared__ TCSShared sh;
-    tc_solve_body<NU, W, SPECG>(P, tc_smem, &tmem_slot, tc_bars, sh);
+    tc_solve_body<NU, W, SPECG, (MINB <= 2)>(P, tc_smem, &tmem_slot, tc_bars, sh);
 }
 
 template <int NU, int W>

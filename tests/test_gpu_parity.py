@@ -420,13 +420,13 @@ def test_tensor_core_solve_teacher_forced_and_free_running(solver, O, vehicle, p
 def test_tensor_core_solve_speculative_build_returns_the_same_bits(solver, monkeypatch):
     """The build with the speculative gradient pass and per-problem phases (few problems per CTA, mpc_tcsolve.cuh) evaluates
     the same expressions on the same operands as the plain build: plans, trajectories, telemetry and the whole decision
-    trace are identical bit for bit — over batch sizes from one problem per CTA up to an eighth of the slots, particles,
+    trace are identical bit for bit — over batch sizes from one problem per CTA up to a quarter of the slots, particles,
     width 64, early stopping (problems leaving at different iterations) and warm-started ticks."""
     cases = [("iris", 1, 40, {}), ("iris", 1, 12, dict(rtol=1e-3, atol=1e-3)), ("hexa", 1, 25, {}), ("hexa", 8, 20, {}), ("iris", 4, 20, {})]
     for veh, Pn, iters, extra in cases:
         cfg, blob, _ = make_setup(veh, "traj", tensor=True, max_iter=iters, num_particles=Pn, **extra)
         tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.0, duration=20.0))
-        for B in (3, 148 + 5, 148 * (16 // Pn)):
+        for B in (3, 148 + 5, 148 * (32 // Pn)):
             x = random_states(B, B + Pn)
             ct = np.linspace(0, 3, B).astype(np.float32)
             rng = np.array([[5, b] for b in range(B)], np.uint64)
