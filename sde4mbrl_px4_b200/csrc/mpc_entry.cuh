@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(WPC * 32, 1) mpc_pcluster_kernel(const __grid_
 
     PC pc;
     pc.gwi = crank * WPC + warp;
-    pc.l = PC::replica_of(pc.gwi);
+    pc.l = pc.gwi / PP;
     pc.p = pc.gwi % PP;
     pc.xc_local = team_base;
     pc.warp_base_local = warp_base;

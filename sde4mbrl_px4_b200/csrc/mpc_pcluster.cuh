@@ -27,12 +27,6 @@ struct PCluster {
     static constexpr int TW = PP * (LSW + SGW);   // warps of the team (<= 64: two exchange values per lane)
     static_assert(TW <= 64 && TW % WPC == 0 && 32 % PP == 0, "team of at most 64 warps, whole CTAs, replicas inside a half");
     static constexpr int CS = TW / WPC;   // CTAs of the cluster
-    // Team-warp index (CTA = index / WPC) of the first warp of replica r.  P = 1 in the wide shape: line-search replica i and
-    // speculation replica i share CTA i — the speculation warp (40 step evaluations, the critical path) then has its SM to
-    // itself once the trial (20) is done, instead of sharing it with another speculation warp throughout.
-    static constexpr bool PAIRED = (PP == 1 && LSW == SGW && WPC == 2);
-    static __device__ __forceinline__ int first_warp(int r) { return PAIRED ? (r < LSW ? 2 * r : 2 * (r - LSW) + 1) : r * PP; }
-    static __device__ __forceinline__ int replica_of(int w) { return PAIRED ? ((w & 1) ? LSW + (w >> 1) : (w >> 1)) : w / PP; }
     int l, p, gwi;                        // replica, particle, warp index in the team
     float* xc_local;                      // this CTA's exchange area: [2 parities][WPC warps][2 floats]
     float* warp_base_local;               // this CTA's per-warp regions
@@ -70,8 +64,8 @@ __device__ __forceinline__ float4 pc_exchange(const PCluster<PP, LSW, SGW, WPC>&
 // mean over the particles of replica r of the first components (sequential sum in particle order, times 1/P); the PP
 // warps of a replica never straddle the two halves of the exchange (PP divides 32)
 template <int PP>
-__device__ __forceinline__ float pc_replica_mean(const float4& v, int w0, float invP) {   // w0: the replica's first team warp
-    const int l0 = w0 & 31;
+__device__ __forceinline__ float pc_replica_mean(const float4& v, int r, float invP) {
+    const int w0 = r * PP, l0 = w0 & 31;
     const float src = w0 < 32 ? v.x : v.z;
     float acc = __shfl_sync(0xffffffffu, src, l0);
 #pragma unroll
@@ -80,7 +74,8 @@ __device__ __forceinline__ float pc_replica_mean(const float4& v, int w0, float 
 }
 // second component published by the first warp of replica r
 template <int PP>
-__device__ __forceinline__ float pc_replica_second(const float4& v, int w0) {
+__device__ __forceinline__ float pc_replica_second(const float4& v, int r) {
+    const int w0 = r * PP;
     return __shfl_sync(0xffffffffu, w0 < 32 ? v.y : v.w, w0 & 31);
 }
 
@@ -90,7 +85,6 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
     const int lane = c.lane;
     const int n = P.H * NU;
     const float invP = __fdiv_rn(1.0f, (float)PP);
-    using PC = PCluster<PP, LSW, SGW, WPC>;
     const int l = pc.l;
     const bool is_spec = l >= LSW;
     const int cand = l - LSW;                                  // speculation candidate of this replica (if is_spec)
@@ -104,10 +98,9 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
     // particle mean of the per-warp gradients (in g2) of replica r -> this warp's c.g
     auto mean_grad = [&](int r) {
         for (int i = lane; i < n; i += 32) {
-            const int w0 = PC::first_warp(r);
-            float a = pc.region(w0)[P.o_g2 + i];
+            float a = pc.region(r * PP)[P.o_g2 + i];
 #pragma unroll
-            for (int q = 1; q < PP; ++q) a = a + pc.region(w0 + q)[P.o_g2 + i];
+            for (int q = 1; q < PP; ++q) a = a + pc.region(r * PP + q)[P.o_g2 + i];
             c.g[i] = a * invP;
         }
         __syncwarp();
@@ -122,7 +115,7 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
             c.g = gsave;
             const float4 v = pc_exchange<PP, LSW, SGW, WPC>(pc, lane, warp_in_cta, xpar, Jw, 0.f);
             xpar ^= 1;
-            fy = pc_replica_mean<PP>(v, PC::first_warp(l), invP);
+            fy = pc_replica_mean<PP>(v, l, invP);
             mean_grad(l);
             if (it == 1) { Jx = fy; init_cost = fy; }
             if (SGW > 0) pc.barrier();   // a speculation warp overwrites its g2 next; its replica's other warps may still be reading it
@@ -189,13 +182,13 @@ __device__ __forceinline__ void apg_solve_pcluster(const KParams& P, Warp<NU, W>
             xpar ^= 1;
             if (round == 0) {
 #pragma unroll
-                for (int cc = 0; cc < SGW; ++cc) fc[cc] = pc_replica_mean<PP>(v, PC::first_warp(LSW + cc), invP);
+                for (int cc = 0; cc < SGW; ++cc) fc[cc] = pc_replica_mean<PP>(v, LSW + cc, invP);
             }
             int q = 0;
             float Jq = 0.f;
             for (; q < LSW && base + q <= P.maxls; ++q) {
-                Jq = pc_replica_mean<PP>(v, PC::first_warp(q), invP);
-                const float dq = pc_replica_second<PP>(v, PC::first_warp(q));
+                Jq = pc_replica_mean<PP>(v, q, invP);
+                const float dq = pc_replica_second<PP>(v, q);
                 if (Jq <= fma_(P.coef, dq, fy)) { ok = true; break; }
             }
             if (ok) { jsel = base + q; Jp = Jq; break; }
