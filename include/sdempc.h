@@ -63,7 +63,8 @@ extern "C" {
                                       particles: network layers and their adjoints on the tensor cores (tcgen05, TF32 operands, fp32         \
                                       accumulation, tanh.approx), the whole APG loop on that mapping (mpc_tcsolve.cuh).  NOT bit-identical   \
                                       to the FP32 path: compared with the oracle teacher-forced and at cost level within the bound stated    \
-                                      in DESIGN.md section 5.2.  Refuses the soft input-rate constraint.  Pays off from a few thousand        \
+                                      in DESIGN.md section 5.2.  The solve takes the soft input-rate constraint (a build of its own), the        \
+                                      rollout entry point refuses it.  Pays off from a few thousand                                           \
                                       rollout rows (problems x particles) per launch; a single tick stays on the FP32 kernels. */
 /* Default kernel choice: latency kernels when the batch fits one problem per SM (or per cluster), the throughput
  * kernel for large batches (> ~13 problems per SM; P = 1, width 32), one warp per (problem, particle) otherwise.

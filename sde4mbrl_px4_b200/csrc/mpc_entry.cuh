@@ -42,6 +42,7 @@ struct KernelChoice {
     void (*rollout_tc_grad)(KParams);   // ... with the adjoint sweep
     void (*solve_tc)(KParams);     // tensor-core batched APG solve, SDEMPC_F_TENSOR
     void (*solve_tc_spec)(KParams);// ... with the speculative gradient pass (few problems per CTA)
+    void (*solve_tc_rate)(KParams);// ... with the soft input-rate constraint
     void (*solve_tc_lat)(KParams); // ... built for two CTAs per SM (more registers): small and medium batches
     int tc_bytes, tc_bytes_grad, tc_tape_granules, tc_bytes_solve, tc_solve_tape_granules, tc_cols;
     int gp;
@@ -568,7 +569,7 @@ KernelChoice make_choice() {
     k.solve_cl = k.closed_cl = nullptr;
     k.solve_group = nullptr;
     k.solve_pc = k.solve_pcw = nullptr;
-    k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = nullptr;
+    k.rollout_tc = k.rollout_tc_grad = k.solve_tc = k.solve_tc_lat = k.solve_tc_spec = k.solve_tc_rate = nullptr;
     k.tc_bytes = k.tc_bytes_grad = k.tc_tape_granules = k.tc_bytes_solve = k.tc_solve_tape_granules = k.tc_cols = 0;
     if constexpr (PP == 2 || PP == 4 || PP == 8) k.solve_pc = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP), PC_WPC>;
     if constexpr (PP == 1 || PP == 2 || PP == 4 || PP == 8) k.solve_pcw = mpc_pcluster_kernel<NU, W, PP, pc_lsw(PP), pc_sgw(PP), pcw_wpc(PP)>;

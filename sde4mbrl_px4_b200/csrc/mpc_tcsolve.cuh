@@ -110,7 +110,9 @@ __device__ __forceinline__ void softplus_sigmoid_fast(float s, float& sp, float&
 // PFR = true (the builds with the register budget of two CTAs per SM): the operands of step t + 1 (controls, gradient, x_k,
 // noise, reference row: 31-35 values per row) are loaded into registers at the top of step t — a full step ahead of their
 // use — instead of being prefetched towards L1 and loaded when needed (which still exposes an L1 / L2 round trip per step).
-template <int NU, int W, bool SPECG, bool PFR>
+// RATE = true: the build that evaluates the soft input-rate constraint (u_slew_constr; a run-time branch for it in every build
+// costs the four-CTA build 6 % — 32 more bytes of spill — for a feature one reference configuration uses).
+template <int NU, int W, bool SPECG, bool PFR, bool RATE>
 __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* sB, uint32_t* tmem_base_slot, uint64_t* bars,
                                               TCSShared& sh) {
     using L = TCSLayout<NU, W>;
@@ -620,6 +622,15 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
             }
             Jp = fma_(disc, l, Jp);
             disc = disc * P.discount;
+            if (RATE && SDEMPC_RATE_ON(P)) {   // soft input-rate constraint (rate_cost in mpc_kernels.cuh): w_t e^2, e the violation of [lo, hi] by u_t - u_{t-1}
+                const float wt = P.rate_w[t];
+#pragma unroll
+                for (int i = 0; i < NU; ++i) {
+                    const float ds = u[i] - up[i];
+                    const float e = ds > P.slew_hi[i] ? ds - P.slew_hi[i] : (ds < P.slew_lo[i] ? ds - P.slew_lo[i] : 0.f);
+                    Jp = fma_(wt * e, e, Jp);
+                }
+            }
 #pragma unroll
             for (int i = 0; i < NU; ++i) up[i] = u[i];
 #pragma unroll
@@ -858,6 +869,21 @@ __device__ __forceinline__ void tc_solve_body(const KParams& P, unsigned char* s
                     for (int i = 0; i < NIN; ++i) lz[i] = o[i];
                 }
                 bwd_post<NU>(P, xt, u, up, mid, lz, gu, gp, lam);
+                if (RATE && SDEMPC_RATE_ON(P)) {   // its gradient (rate_grad_add): 2 w_t e_t - 2 w_{t+1} e_{t+1}
+                    const float* yt = YK + q + t * (NU * RS);
+                    const float wt = 2.f * P.rate_w[t], wn = (t + 1 < P.H) ? 2.f * P.rate_w[t + 1] : 0.f;
+#pragma unroll
+                    for (int i = 0; i < NU; ++i) {
+                        const float hi = P.slew_hi[i], lo = P.slew_lo[i];
+                        const float ds = u[i] - up[i];
+                        float a = wt * (ds > hi ? ds - hi : (ds < lo ? ds - lo : 0.f));
+                        if (t + 1 < P.H) {
+                            const float dn = yt[(NU + i) * RS] - u[i];
+                            a = a - wn * (dn > hi ? dn - hi : (dn < lo ? dn - lo : 0.f));
+                        }
+                        gu[i] = gu[i] + a;
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < NU; ++i) {
                     const float gm = pmean(gu[i]);

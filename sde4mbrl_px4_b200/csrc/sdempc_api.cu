@@ -77,7 +77,7 @@ static const std::vector<KernelChoice>& choices() {
         };
         for (auto& k : c)
             if (const TCKernels* t = tc_kernels(k.nu, k.W)) {   // one set of tensor-core kernels per (nu, width): the particle count is a run-time row mapping
-                k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve; k.solve_tc_lat = t->solve_lat; k.solve_tc_spec = t->solve_spec;
+                k.rollout_tc = t->rollout; k.rollout_tc_grad = t->rollout_grad; k.solve_tc = t->solve; k.solve_tc_lat = t->solve_lat; k.solve_tc_spec = t->solve_spec; k.solve_tc_rate = t->solve_rate;
                 k.tc_bytes = t->bytes; k.tc_bytes_grad = t->bytes_grad; k.tc_bytes_solve = t->bytes_solve;
                 k.tc_tape_granules = t->tape_granules; k.tc_solve_tape_granules = t->solve_tape_granules; k.tc_cols = t->cols;
             }
@@ -123,12 +123,12 @@ struct sdempc_handle {
     int sm_count = 0;
     int64_t launches = 0;
     int last_grid = 0;
-    int regs = 0, regs_tc = 0, regs_tc_lat = 0, regs_tc_spec = 0;
+    int regs = 0, regs_tc = 0, regs_tc_lat = 0, regs_tc_spec = 0, regs_tc_rate = 0;
     int pcw_clusters = 0;                                 // clusters of the wide shape of the cluster latency kernel the device holds at once
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_pcw = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_pcw = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false, staged_tc_rate = false;
     float last_ms = 0.f;
 };
 
@@ -378,10 +378,12 @@ static int ensure_device(sdempc_handle* h) {
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
         CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
+        CUDA_TRY(cudaFuncSetAttribute(h->kc.solve_tc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, h->kc.tc_bytes_solve));
         cudaFuncAttributes ft;
         CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc)); h->regs_tc = ft.numRegs;
         CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc_lat)); h->regs_tc_lat = ft.numRegs;
         CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc_spec)); h->regs_tc_spec = ft.numRegs;
+        CUDA_TRY(cudaFuncGetAttributes(&ft, h->kc.solve_tc_rate)); h->regs_tc_rate = ft.numRegs;
         CUDA_TRY(cudaMalloc(&h->d_wimg_tc, h->wimg_tc.size() * 4));
         CUDA_TRY(cudaMemcpy(h->d_wimg_tc, h->wimg_tc.data(), h->wimg_tc.size() * 4, cudaMemcpyHostToDevice));
     }
@@ -561,8 +563,8 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     if ((rc = ensure_io(h, in_bytes, out_bytes))) return rc;
     // SDEMPC_F_TENSOR: the batched solve on the tensor-core mapping (explicit opt-in: TF32 products, not SPEC-ARITH)
     const bool tcs = (h->cfg.flags & SDEMPC_F_TENSOR) != 0;
-    if (tcs && (!h->kc.solve_tc || P > 32 || (P & (P - 1)) != 0 || h->cfg.u_slew_constr_coeff != 0.0f))
-        return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core solve supports 1, 2, 4, ... 32 particles and no input-rate constraint");
+    if (tcs && (!h->kc.solve_tc || P > 32 || (P & (P - 1)) != 0))
+        return fail(SDEMPC_EINVAL, "SDEMPC_F_TENSOR: the tensor-core solve supports 1, 2, 4, ... 32 particles");
     const bool pclw = !tcs && use_pcluster_wide(h, B), pcl = !tcs && (pclw || use_pcluster(h, B));
     const bool spec = !tcs && !pcl && use_spec(h, B), group = !tcs && use_group(h, B), cl = !tcs && !pcl && use_cluster(h, B);
     // throughput kernel: enough CTAs that a warp holds ~2+ problems when the batch is small, all SMs otherwise
@@ -604,7 +606,8 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     if (tcs) { k.wimg = h->d_wimg_tc; k.tcs_ws = h->d_tcs_ws; k.tcs_ppc = ppc; k.tcs_rs = rs; k.tcs_sms = h->sm_count; }
     h->staged = k; h->staged_B = B; h->staged_ok = true; h->last_grid = grid; h->staged_spec = spec; h->staged_group = group; h->staged_cl = cl; h->staged_pc = pcl; h->staged_pcw = pclw;
     h->staged_tc = tcs; h->staged_tc_lat = tcs && tcs_lat;
-    h->staged_tc_spec = tcs && tcs_lat && h->tcs_spec && ppc * (h->tcs_spec == 2 ? 8 : 4) <= 128 / P;   // (few problems per CTA: speculative gradient passes, mpc_tcsolve.cuh)
+    h->staged_tc_rate = tcs && h->cfg.u_slew_constr_coeff != 0.0f;   // the one build that evaluates the input-rate constraint
+    h->staged_tc_spec = tcs && !h->staged_tc_rate && tcs_lat && h->tcs_spec && ppc * (h->tcs_spec == 2 ? 8 : 4) <= 128 / P;   // (few problems per CTA: speculative gradient passes, mpc_tcsolve.cuh)
     return 0;
 }
 
@@ -627,7 +630,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
     }
     const bool spec = (fn == h->kc.solve_spec || fn == h->kc.closed_spec) && fn != nullptr;
     const bool group = (fn == h->kc.solve_group) && fn != nullptr;
-    const bool tcs = (fn == h->kc.solve_tc || fn == h->kc.solve_tc_lat || fn == h->kc.solve_tc_spec) && fn != nullptr;
+    const bool tcs = (fn == h->kc.solve_tc || fn == h->kc.solve_tc_lat || fn == h->kc.solve_tc_spec || fn == h->kc.solve_tc_rate) && fn != nullptr;
     const int threads = tcs ? 128 : spec ? (SPEC_LSW + SPEC_SGW) * 32 : group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;
     const size_t smem = tcs ? (size_t)h->kc.tc_bytes_solve : spec ? h->smem_bytes_spec : group ? h->smem_bytes_group : h->smem_bytes;
     void* args[] = {const_cast<KParams*>(&k)};
@@ -637,7 +640,7 @@ static int launch(sdempc_handle* h, void (*fn)(KParams), const KParams& k, int g
 }
 
 static void (*staged_kernel(const sdempc_handle* h))(KParams) {
-    return h->staged_tc ? (h->staged_tc_spec ? h->kc.solve_tc_spec : h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pcw ? h->kc.solve_pcw : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
+    return h->staged_tc ? (h->staged_tc_rate ? h->kc.solve_tc_rate : h->staged_tc_spec ? h->kc.solve_tc_spec : h->staged_tc_lat ? h->kc.solve_tc_lat : h->kc.solve_tc) : h->staged_pcw ? h->kc.solve_pcw : h->staged_pc ? h->kc.solve_pc : h->staged_cl ? h->kc.solve_cl : h->staged_spec ? h->kc.solve_spec
            : h->staged_group ? h->kc.solve_group : h->kc.solve;
 }
 
@@ -1056,7 +1059,7 @@ float sdempc_last_launch_ms(const sdempc_t* h) { return h ? h->last_ms : 0.f; }
 int sdempc_kernel_info(sdempc_t* h, int32_t out[6]) {
     if (!h || !out) return fail(SDEMPC_EINVAL, "null argument");
     if (h->staged_tc) {
-        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_spec ? h->regs_tc_spec : h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
+        out[0] = 128; out[1] = h->kc.tc_bytes_solve; out[2] = h->staged.tcs_ppc; out[3] = h->staged_tc_rate ? h->regs_tc_rate : h->staged_tc_spec ? h->regs_tc_spec : h->staged_tc_lat ? h->regs_tc_lat : h->regs_tc; out[4] = h->last_grid; out[5] = h->sm_count;
         return 0;
     }
     out[0] = h->staged_pcw ? pcw_wpc(h->kc.P) * 32 : (h->staged_cl || h->staged_pc) ? SPEC_LSW * 32 : h->staged_spec ? (SPEC_LSW + SPEC_SGW) * 32 : h->staged_group ? GROUP_GW * 32 : h->kc.G * h->kc.P * 32;

@@ -22,13 +22,14 @@ __global__ void __launch_bounds__(128, 512 / TCLayout<NU, W>::COLS) mpc_tc_rollo
 // what tensor memory allows: large batches) and 2 CTAs per SM (164 registers, no spill: 11 % faster per CTA, used while the
 // batch needs at most two CTAs per SM).  SPECG: the build with the speculative gradient pass and per-problem phases
 // (mpc_tcsolve.cuh), for CTAs that own at most a quarter of their slots in problems.
-template <int NU, int W, int MINB, bool SPECG>
+// RATE: with the soft input-rate constraint (one more build, of the plain two-CTA kernel).
+template <int NU, int W, int MINB, bool SPECG, bool RATE = false>
 __global__ void __launch_bounds__(128, MINB) mpc_tc_solve_kernel(const __grid_constant__ KParams P) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(8) uint64_t tc_bars[2];
     __shared__ TCSShared sh;
-    tc_solve_body<NU, W, SPECG, (MINB <= 2)>(P, tc_smem, &tmem_slot, tc_bars, sh);
+    tc_solve_body<NU, W, SPECG, (MINB <= 2), RATE>(P, tc_smem, &tmem_slot, tc_bars, sh);
 }
 
 template <int NU, int W>
@@ -40,6 +41,7 @@ static TCKernels make_tc() {
     k.solve = mpc_tc_solve_kernel<NU, W, 512 / L::COLS, false>;
     k.solve_lat = (512 / L::COLS > 2) ? mpc_tc_solve_kernel<NU, W, 2, false> : k.solve;
     k.solve_spec = mpc_tc_solve_kernel<NU, W, 2, true>;
+    k.solve_rate = mpc_tc_solve_kernel<NU, W, 2, false, true>;
     // Residency must be bounded by tensor memory (512 / COLS CTAs per SM), never exceed it: a CTA that the block
     // scheduler places beyond that spins in tcgen05.alloc while holding its slot (width 64, forward variant:
     // registers and shared memory allowed three CTAs, tensor memory two -- launches were bimodal, 0.30 / 0.41 ms).

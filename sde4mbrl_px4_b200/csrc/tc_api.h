@@ -11,6 +11,7 @@ struct TCKernels {
     void (*rollout_grad)(KParams);   // ... with the adjoint sweep
     void (*solve)(KParams);          // batched APG solve (mpc_tcsolve.cuh), register budget for 512 / cols CTAs per SM
     void (*solve_spec)(KParams);     // two-CTA register budget + speculative gradient pass: at most slots / 4 problems per CTA
+    void (*solve_rate)(KParams);     // two-CTA register budget + the soft input-rate constraint (u_slew_constr configurations)
     void (*solve_lat)(KParams);      // same kernel with the register budget of two CTAs per SM (== solve when cols = 256)
     int bytes, bytes_grad, bytes_solve;   // dynamic shared memory of each (already padded so that residency <= tensor memory)
     int tape_granules;               // rollout_grad: 16-byte tape granules per row and step

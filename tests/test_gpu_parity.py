@@ -256,6 +256,45 @@ def test_soft_slew_rate_constraint(solver, O, mode):
     assert not np.array_equal(c[0], b[0])
 
 
+@pytest.mark.parametrize("particles", [1, 4])
+def test_tensor_core_solve_soft_slew_rate_constraint(solver, O, particles):
+    """The same tightened rate constraint under SDEMPC_F_TENSOR: the first iteration (same y on both sides) has the oracle's
+    cost and squared gradient norm within the TF32 bound — the constraint's cost and its gradient are in — and the solve ends
+    at the oracle's cost level, away from where it ends without the constraint."""
+    import os
+
+    from conftest import ROOT
+    from sde4mbrl_px4_b200 import config, model_io
+
+    cfgd = config.load_yaml(os.path.join(ROOT, "configs", "iris_pos.yaml"))
+    cfgd["cost_params"]["u_slew_constr"] = [[-0.01, 0.004], [-0.02, 0.01], [-29, 0.002], [-0.005, 0.25]]
+    cfgd["apg_mpc"].update(max_iter=40)
+    cfg_t = config.build_config(cfgd, tensor=True, num_particles=particles)
+    cfg = config.build_config(cfgd, num_particles=particles)
+    blob = model_io.synthetic_model("iris").to_blob()
+    s, o = solver.MPCSolver(cfg_t, blob), O.Oracle(cfg, blob, "f32")
+    B = 150          # one and two problems per CTA
+    pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=78)
+    u0, i0 = s.reset(B)
+    uq = np.clip(u0 + 0.05 * np.random.default_rng(3).standard_normal(u0.shape), 1e-4, 1).astype(np.float32)
+    xdes = pr["xref_win"][:, 0]
+    a = s.solve(pr["x"], uq, i0, xdes=xdes, rng=pr["rng"], want_trace=True)
+    b = o.solve(pr["x"], uq, i0, xdes=xdes, rng=pr["rng"], want_trace=True)
+    rel = lambda x, y: np.abs(x - y) / np.maximum(np.abs(y), 1e-12)
+    assert rel(a[3][:, 0, 0], b[3][:, 0, 0]).max() <= 2e-3, "f_y of the first iteration"
+    assert rel(a[3][:, 0, 6], b[3][:, 0, 6]).max() <= 5e-3, "|g|^2 of the first iteration"
+    rc = rel(a[2][:, 6], b[2][:, 6])
+    assert np.median(rc) <= 2e-3 and np.quantile(rc, 0.9) <= 2e-2, (np.median(rc), np.quantile(rc, 0.9), rc.max())
+    # the constraint matters and the tensor-core solve follows it: on the problems whose final cost it moves by more than
+    # 1 %, the tensor-core result lies with the constrained oracle, not with the unconstrained one
+    cfg.u_slew_constr_coeff = 0.0
+    c = O.Oracle(cfg, blob, "f32").solve(pr["x"], uq, i0, xdes=xdes, rng=pr["rng"])
+    moved = rel(c[2][:, 6], b[2][:, 6]) > 1e-2
+    assert moved.sum() >= 10, moved.sum()
+    near = np.abs(a[2][:, 6] - b[2][:, 6])[moved] < 0.25 * np.abs(c[2][:, 6] - b[2][:, 6])[moved]
+    assert near.mean() >= 0.9, (moved.sum(), near.mean())
+
+
 @pytest.mark.parametrize("vehicle,scale,tol", [("iris", None, 1e-4), ("hexa", None, 1e-4), ("iris", 0.6, 5e-3)])
 def test_tensor_core_rollout_within_stated_tolerance(solver, O, vehicle, scale, tol):
     """SDEMPC_F_TENSOR: the batched value_and_grad with the network layers on the tensor cores (tcgen05, TF32
