@@ -58,7 +58,7 @@ extern "C" {
 #define SDEMPC_F_SPECULATIVE_LS 4u /* force latency mode: all line-search trials evaluated concurrently on sibling warps */
 #define SDEMPC_F_SEQUENTIAL_LS 8u  /* force the one-warp-per-problem kernel (sequential line search) */
 #define SDEMPC_F_GROUP 16u         /* force the throughput kernel (several problems per warp) */
-#define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a 2-CTA cluster */
+#define SDEMPC_F_NO_CLUSTER 32u    /* latency kernel on one SM (8 warps) instead of a thread-block cluster of 2-16 SMs */
 #define SDEMPC_F_TENSOR 64u        /* batched sdempc_solve_ex / sdempc_solve (m_mpc) and sdempc_rollout (value_and_grad) with 1, 2, 4 ... 32       \
                                       particles: network layers and their adjoints on the tensor cores (tcgen05, TF32 operands, fp32         \
                                       accumulation, tanh.approx), the whole APG loop on that mapping (mpc_tcsolve.cuh).  NOT bit-identical   \
