@@ -557,11 +557,13 @@ def test_tensor_core_solve_modes_and_batches(solver, O):
     c = sn.solve(xb, un, in_, xref_win=prn["xref_win"], xi=xi)
     assert np.isinf(c[2][3, 6]) and c[2][3, 2] == 1 and np.all(np.isfinite(np.delete(c[2][:, 6], 3)))
     assert np.array_equal(np.delete(c[0], 3, axis=0), np.delete(a[0], 3, axis=0))
-    # what the tensor-core solve does not implement is refused, never served by another path
+    # the position-control configuration carries the soft input-rate constraint: served by the build that evaluates it
+    # (test_tensor_core_solve_soft_slew_rate_constraint checks the arithmetic)
     cfgr, blobr, _ = make_setup("iris", "pos", tensor=True)
     assert cfgr.u_slew_constr_coeff != 0.0
-    with pytest.raises(RuntimeError, match="SDEMPC_F_TENSOR"):
-        solver.MPCSolver(cfgr, blobr).solve(x, u0, i0, xdes=xd, rng=rng)
+    sr = solver.MPCSolver(cfgr, blobr)
+    r = sr.solve(x, u0, i0, xdes=xd, rng=rng)
+    assert np.all(np.isfinite(r[0])) and np.all(r[2][:, 6] <= r[2][:, 5]) and sr.kernel_info()["regs_per_thread"] > 128
 
 
 @pytest.mark.parametrize("seed", list(range(24)))
