@@ -11,9 +11,11 @@ iteration counts are identical everywhere).  Per-GPU work is fixed as N grows: w
 on the data path; the only exchange is the final result gather, which is inside the e2e region.
   value  : solves/s with inputs resident in HBM, CUDA-event time of the K launches on the launching stream,
            L2 flushed between launches, max over ranks.
-  e2e    : the same metric through the public API (`MPCSolver.solve` == the C ABI `sdempc_solve_ex`) with HOST
-           buffers: H2D of the step's inputs from pinned staging, the launch, D2H of plan + trajectory +
-           telemetry, and for N > 1 the result gather to rank 0.
+  e2e    : the same metric through the public API (`MPCSolver.solve_pinned` == the C ABI `sdempc_solve_ex` on the
+           caller's page-locked HOST buffers: the library copies straight between them and the device): H2D of the
+           step's inputs, the launch, D2H of plan + trajectory + telemetry, and for N > 1 the result gather to rank 0
+           (`sharding.solve_sharded`).  `e2e.pageable_arrays_value`: the same through `MPCSolver.solve` with plain numpy
+           arrays (one more host copy each way through the library's pinned staging blocks).
   latency_ms : BASELINE config 2, single iris tick (B=1) warm-started along a trajectory, p50/p99/max, both
            end to end (host call -> result in host memory, the reference's own definition of solve time,
            sde_control.py:386-425) and device only; `hexa_p8` = BASELINE config 3 as a single tick.
@@ -294,29 +296,44 @@ def main():
         h2d = pr["x"].nbytes + u0.nbytes + i0.nbytes + pr["xref_win"].nbytes + pr["rng"].nbytes
         d2h = u.nbytes + xe.nbytes + info.nbytes
         ue = None
-        for _ in range(2):
+        pb = None
+        if dist is not None:   # N > 1: this rank's (constant) inputs page-locked in place: solve_sharded sends them by DMA
+            s.pin(pr["x"], pr["xref_win"], pr["rng"])
+        if dist is None:   # one GPU: the caller's buffers are page-locked (MPCSolver.pinned_batch), the library copies straight
+            pb = s.pinned_batch(B, window=True)     # between them and the device: same C call (sdempc_solve_ex), no staging copy
+            pb.x[:] = pr["x"]; pb.xref[:] = pr["xref_win"]; pb.rng[:] = pr["rng"]
+
+        def one_step():
             if dist is None:
-                s.solve(pr["x"], u0, i0, **kw)
-            else:
-                sharding.solve_sharded(s, pr, u0, i0, world * B)
+                pb.u[:] = u0; pb.info[:] = i0       # the solve works in place: this step's plan and telemetry inputs
+                return s.solve_pinned(pb)[0]
+            # H2D + solve + result gather to rank 0 through shared memory (no collective on the data path) + D2H
+            g = sharding.solve_sharded(s, pr, u0, i0, world * B)
+            return g["u"][:B] if rank == 0 else None
+
+        for _ in range(2):
+            one_step()
         barrier()
         sampler.start()
         t0 = time.perf_counter()
         for _ in range(timed_steps):
-            if dist is None:
-                ue, _, _, _ = s.solve(pr["x"], u0, i0, **kw)
-            else:   # H2D + solve + device-to-device result gather to rank 0 (the only collective) + D2H there
-                g = sharding.solve_sharded(s, pr, u0, i0, world * B)
-                if rank == 0:
-                    ue = g["u"][:B]
+            ue = one_step()
         barrier()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         sampler.stop()
         if rank == 0:
             assert np.array_equal(ue, u), "e2e solve and staged solve disagree"
+        e2e_pageable = None
+        if dist is None:   # for comparison: the same through MPCSolver.solve with pageable numpy arrays (staging copies on the host)
+            t0 = time.perf_counter()
+            for _ in range(timed_steps):
+                s.solve(pr["x"], u0, i0, **kw)
+            e2e_pageable = B * timed_steps / (time.perf_counter() - t0)
+            pb.close()
         return dict(cfg=cfg, blob=blob, pr=pr, s=s, info=info, B=B, value=world * B * timed_steps / (dev_ms * 1e-3),
                     ms_per_step=dev_ms / timed_steps, kern_ms=float(ms.mean()), launches=int(launches),
-                    e2e_value=world * B * timed_steps / e2e_s, e2e_ms=e2e_s / timed_steps * 1e3, h2d=int(h2d), d2h=int(d2h))
+                    e2e_value=world * B * timed_steps / e2e_s, e2e_ms=e2e_s / timed_steps * 1e3, h2d=int(h2d), d2h=int(d2h),
+                    e2e_pageable=e2e_pageable)
 
     B_weak, B_strong = args.batch, max(1, args.batch // world)
     main_B = B_weak if args.scaling == "weak" else B_strong
@@ -535,7 +552,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, args, per_gpu=B),
             "e2e": {"value": r["e2e_value"], "unit": "solves/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                    "ms_per_step": r["e2e_ms"]},
+                    "ms_per_step": r["e2e_ms"],
+                    "api": "MPCSolver.solve_pinned: sdempc_solve_ex on page-locked caller buffers (N = 1); "
+                           "sharding.solve_sharded (N > 1)",
+                    "pageable_arrays_value": r["e2e_pageable"]},
             "gpu_launches": r["launches"], "gpu_launches_e2e": int(args.steps),
             "roofline": roofline, "cpu_baseline": cb, "latency_ms": latency, "clocks": sampler.summary(),
             "kernel_info": ki, ("strong_scaling" if args.scaling == "weak" else "weak_scaling"): other,

@@ -128,7 +128,7 @@ struct sdempc_handle {
     // staged launch
     KParams staged;
     int staged_B = 0;
-    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_pcw = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false, staged_tc_rate = false;
+    bool staged_ok = false, staged_spec = false, staged_group = false, staged_cl = false, staged_pc = false, staged_pcw = false, staged_direct_in = false, staged_tc = false, staged_tc_lat = false, staged_tc_spec = false, staged_tc_rate = false;
     float last_ms = 0.f;
 };
 
@@ -514,14 +514,32 @@ static int ensure_io(sdempc_handle* h, size_t in_bytes, size_t out_bytes) {
     return 0;
 }
 
-// Sequential packer of 16-byte aligned sub-buffers into the pinned IN block.
+// is p page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. through sdempc_host_register)?
+static bool is_pinned(const void* p) {
+    if (p == nullptr) return true;
+    cudaPointerAttributes at;
+    const bool ok = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    return ok;
+}
+
+// Sequential packer of 16-byte aligned sub-buffers into the device IN block.
+// Inputs of a call are packed into one pinned staging block and sent with one copy — or, when the caller passes page-locked
+// arrays (direct != nullptr), every array goes with its own asynchronous copy: straight from the caller's memory if it is
+// page-locked, from its slot of the staging block otherwise.
 struct Packer {
     char* hbase; char* dbase; size_t off = 0;
+    cudaStream_t direct = nullptr;
+    bool failed = false, all_direct = true;
     template <typename T>
     const T* put(const T* src, size_t count) {
         if (src == nullptr) return nullptr;
         const size_t bytes = count * sizeof(T);
-        if (hbase) memcpy(hbase + off, src, bytes);
+        if (direct) {
+            const void* from = src;
+            if (!is_pinned(src)) { memcpy(hbase + off, src, bytes); from = hbase + off; all_direct = false; }
+            failed |= cudaMemcpyAsync(dbase + off, from, bytes, cudaMemcpyHostToDevice, direct) != cudaSuccess;
+        } else if (hbase) memcpy(hbase + off, src, bytes);
         const T* d = reinterpret_cast<const T*>(dbase + off);
         off += (bytes + 15) & ~(size_t)15;
         return d;
@@ -587,6 +605,9 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     }
     KParams k = group ? h->kp_group : h->kp;
     Packer pk{h->h_in, h->d_in};
+    // zero-copy staging: the large inputs page-locked by the caller (sdempc_host_register) go by DMA straight from its memory
+    const bool any_pinned = (a->x && is_pinned(a->x)) || (use_win && is_pinned(a->xref_win)) || (a->xi_override && is_pinned(a->xi_override));
+    if (any_pinned) pk.direct = h->stream;
     k.B = B;
     k.x = pk.put(a->x, (size_t)B * NX);
     k.u_plan = const_cast<float*>(pk.put(a->u_plan, (size_t)B * n));
@@ -596,7 +617,9 @@ static int stage_solve(sdempc_handle* h, const sdempc_solve_args* a) {
     k.xdes = (!use_win && !use_t) ? pk.put(a->xdes, (size_t)B * NX) : nullptr;
     k.xi_override = a->xi_override ? pk.put(a->xi_override, (size_t)B * P * H * 6) : nullptr;
     k.rng = a->xi_override ? nullptr : reinterpret_cast<const unsigned long long*>(pk.put(a->rng, (size_t)B * 2));
-    CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, pk.off, cudaMemcpyHostToDevice, h->stream));
+    if (pk.failed) { CUDA_TRY(cudaGetLastError()); return fail(SDEMPC_ECUDA, "copy from page-locked caller memory failed"); }
+    h->staged_direct_in = any_pinned;
+    if (!any_pinned) CUDA_TRY(cudaMemcpyAsync(h->d_in, h->h_in, pk.off, cudaMemcpyHostToDevice, h->stream));
     Packer po{nullptr, h->d_out};
     k.x_evol = po.reserve<float>((size_t)B * (H + 1) * NX);
     k.u_plan_out = po.reserve<float>((size_t)B * n);
@@ -807,7 +830,10 @@ int sdempc_reset(sdempc_t* h, int B, const float* x, const float* xdes, float* u
 
 int sdempc_stage(sdempc_t* h, const sdempc_solve_args* args) {
     if (!h) return fail(SDEMPC_EINVAL, "null handle");
-    return stage_solve(h, args);
+    const int rc = stage_solve(h, args);
+    // page-locked inputs are read by asynchronous copies: the caller may reuse them as soon as this returns
+    if (rc == 0 && h->staged_direct_in) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return rc;
 }
 
 int sdempc_launch_timed(sdempc_t* h, int n, int flush_l2, float* ms) {
@@ -888,7 +914,9 @@ int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* a) {
     CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
     if ((rc = launch(h, staged_kernel(h), h->staged, h->last_grid))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
-    if ((rc = fetch_solve(h, a))) return rc;   // synchronises the stream
+    // results straight into the caller's memory when it is page-locked (and no trace is asked for), through the staging block otherwise
+    const bool direct_out = !a->trace && is_pinned(a->x_evol) && is_pinned(a->u_plan) && is_pinned(a->info);
+    if ((rc = fetch_solve(h, a, direct_out))) return rc;   // synchronises the stream
     float t = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&t, h->ev0, h->ev1));
     h->last_ms = t;

@@ -45,6 +45,7 @@ class MPCSolver:
         self._check(self.lib.sdempc_create(C.byref(cfg), buf, len(model_blob), device, C.byref(self._h)))
         self.has_trajectory = False
         self._staged = None
+        self._pinned = []
 
     # ------------------------------------------------------------------ helpers
     def _check(self, rc: int):
@@ -52,6 +53,9 @@ class MPCSolver:
             raise RuntimeError(f"sdempc error {rc}: {self.lib.sdempc_last_error().decode()}")
 
     def close(self):
+        for a in getattr(self, "_pinned", []):
+            self.lib.sdempc_host_unregister(a.ctypes.data)
+        self._pinned = []
         if getattr(self, "_h", None):
             self.lib.sdempc_destroy(self._h)
             self._h = C.c_void_p()
@@ -107,6 +111,31 @@ class MPCSolver:
         a, keep = self._args(x, u_plan, info, curr_t, xdes, xref_win, rng, xi, want_trace)
         self._check(self.lib.sdempc_solve_ex(self._h, C.byref(a)))
         return keep["u"], keep["xe"], keep["info"], keep["trace"]
+
+    # ------------------------------------------------------------------ zero-copy batches
+    def pin(self, *arrays) -> bool:
+        """Page-lock caller arrays in place (sdempc_host_register): ``solve`` / ``stage`` then send them by DMA straight from
+        their memory instead of through the staging block.  Released by ``close``.  False if any registration failed."""
+        ok = True
+        for a in arrays:
+            if a is None:
+                continue
+            if self.lib.sdempc_host_register(a.ctypes.data, a.nbytes) == 0:
+                self._pinned.append(a)
+            else:
+                ok = False
+        return ok
+
+    def pinned_batch(self, B: int, window: bool = True) -> "PinnedBatch":
+        """Page-locked buffers for ``solve_pinned``: the library then copies straight between them and the device, with no
+        staging copy on the host.  ``window``: explicit reference windows (``xref``) instead of trajectory times (``curr_t``)."""
+        return PinnedBatch(self, B, window)
+
+    def solve_pinned(self, pb: "PinnedBatch"):
+        """``m_mpc`` on a PinnedBatch, in place: reads pb.x, pb.u (plan, shifted by the solve), pb.info, pb.xref | pb.curr_t,
+        pb.rng; writes pb.u, pb.xe, pb.info.  Same call (sdempc_solve_ex) and same results as ``solve``."""
+        self._check(self.lib.sdempc_solve_ex(self._h, C.byref(pb.args)))
+        return pb.u, pb.xe, pb.info
 
     def rollout(self, x, u, u_prev, curr_t=None, xdes=None, xref_win=None, rng=None, xi=None, want_grad=True):
         """value_and_grad of the MPC objective at ``u``: (cost[B], grad[B,H,nu]|None, x_evol[B,H+1,13])."""
@@ -194,3 +223,43 @@ class MPCSolver:
         self._check(self.lib.sdempc_kernel_info(self._h, C.byref(out)))
         keys = ("threads_per_cta", "smem_bytes", "problems_per_cta", "regs_per_thread", "ctas", "sm_count")
         return dict(zip(keys, [int(v) for v in out]))
+
+
+class PinnedBatch:
+    """Caller-side buffers of one batched solve, page-locked through sdempc_host_register (plain pageable arrays if the
+    registration fails: the call still works, through the staging copies)."""
+
+    def __init__(self, solver: MPCSolver, B: int, window: bool = True):
+        self._lib = solver.lib
+        H, nu = solver.H, solver.nu
+        self.x = np.zeros((B, 13), np.float32)
+        self.u = np.zeros((B, H, nu), np.float32)
+        self.info = np.zeros((B, 8), np.float32)
+        self.xref = np.zeros((B, H + 1, 13), np.float32) if window else None
+        self.curr_t = None if window else np.zeros((B,), np.float32)
+        self.rng = np.zeros((B, 2), np.uint64)
+        self.xe = np.zeros((B, H + 1, 13), np.float32)
+        self._registered = []
+        for a in (self.x, self.u, self.info, self.xref, self.curr_t, self.rng, self.xe):
+            if a is not None and self._lib.sdempc_host_register(a.ctypes.data, a.nbytes) == 0:
+                self._registered.append(a)
+        self.pinned = len(self._registered) == 6
+        a = _abi.SolveArgs()
+        a.B = B
+        a.x, a.curr_t, a.xdes, a.xref_win = _fp(self.x), _fp(self.curr_t), None, _fp(self.xref)
+        a.rng = self.rng.ctypes.data_as(C.POINTER(C.c_uint64))
+        a.u_plan, a.x_evol = _fp(self.u), _fp(self.xe)
+        a.info = self.info.ctypes.data_as(C.POINTER(_abi.Info))
+        a.xi_override, a.trace = None, None
+        self.args = a
+
+    def close(self):
+        for a in self._registered:
+            self._lib.sdempc_host_unregister(a.ctypes.data)
+        self._registered = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -168,6 +168,50 @@ def test_three_kernels_agree(solver, O, vehicle, width, monkeypatch):
         _eq(info[:, :7], infoo[:n, :7], f"telemetry {mode}"); _eq(tr, tro[:n], f"trace {mode}")
 
 
+def test_zero_copy_pinned_batch_matches_solve(solver):
+    """MPCSolver.solve_pinned (the caller's page-locked buffers, DMA straight from / into them — no staging copy) returns the
+    bits of MPCSolver.solve, for a single tick and for a batch, over two warm-started ticks; trajectory-time and explicit-window
+    selections; a staged solve (sdempc_stage + launch + fetch) from page-locked inputs as well."""
+    cfg, blob, _ = make_setup("iris", "traj", max_iter=15)
+    s = solver.MPCSolver(cfg, blob)
+    tab = trajectory.csv_rows_to_table(trajectory.lemniscate(2.0, 8.0, 0.0, duration=20.0))
+    s.set_trajectory(tab)
+    for B, window in ((1, False), (300, True), (300, False)):
+        pr = synthetic.batched_problems(B, cfg.horizon, np.array(cfg.dt[: cfg.horizon]), seed=5 + B)
+        ct = np.linspace(0, 3, B).astype(np.float32)
+        kw = dict(xref_win=pr["xref_win"]) if window else dict(curr_t=ct)
+        pb = s.pinned_batch(B, window=window)
+        assert pb.pinned
+        pb.x[:] = pr["x"]; pb.rng[:] = pr["rng"]
+        if window:
+            pb.xref[:] = pr["xref_win"]
+        else:
+            pb.curr_t[:] = ct
+        u, i = s.reset(B)
+        pb.u[:] = u; pb.info[:] = i
+        for tick in range(2):
+            u, xe, i, _ = s.solve(pr["x"], u, i, rng=pr["rng"], **kw)
+            up, xep, ip = s.solve_pinned(pb)
+            assert np.array_equal(up, u) and np.array_equal(xep, xe) and np.array_equal(ip[:, :7], i[:, :7])
+        # pageable and page-locked arrays mixed in one call (MPCSolver.pin on some of the caller's own arrays)
+        if window and tick == 1:
+            xs, ws = pr["x"].copy(), pr["xref_win"].copy()
+            assert s.pin(xs, ws)
+            m = s.solve(xs, u, i, rng=pr["rng"], xref_win=ws)
+            n_ = s.solve(pr["x"], u, i, rng=pr["rng"], xref_win=pr["xref_win"])
+            assert np.array_equal(m[0], n_[0]) and np.array_equal(m[1], n_[1])
+        # staged path from page-locked inputs: the inputs may be overwritten as soon as stage() returns
+        if window:
+            pb.u[:] = u; pb.info[:] = i
+            want = s.solve(pr["x"], u, i, rng=pr["rng"], **kw)
+            s.stage(pb.x, pb.u, pb.info, xref_win=pb.xref, rng=pb.rng)
+            pb.x[:] = 0; pb.xref[:] = 0
+            s.launch_timed(1, flush_l2=False)
+            got = s.fetch()
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        pb.close()
+
+
 @pytest.mark.parametrize("vehicle,P", [("iris", 2), ("iris", 4), ("iris", 8), ("hexa", 8)])
 def test_particle_cluster_kernel(solver, O, vehicle, P, monkeypatch):
     """P > 1 latency kernel (one problem per thread-block cluster: line-search and speculative-gradient replicas of P particle
