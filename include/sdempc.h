@@ -185,7 +185,11 @@ int sdempc_reset(sdempc_t* h, int B, const float* x, const float* xdes,
 /* m_mpc(x, rng, opt_state, curr_t=, xdes=) -> (uopt, opt_state, rng, x_evol)
  * (sde_control.py:400-416, 713-719).  Host buffers in, host buffers out,
  * synchronous: returns when the results are in the caller's memory, i.e. the
- * reference's `.block_until_ready()` point (sde_control.py:420).             */
+ * reference's `.block_until_ready()` point (sde_control.py:420).
+ * Zero-copy staging: arrays the caller has page-locked (sdempc_host_register,
+ * cudaHostAlloc) are copied straight between its memory and the device; pageable
+ * arrays go through the library's pinned staging blocks (one more host copy each
+ * way).  Detected per call (cudaPointerGetAttributes); same results either way.  */
 int sdempc_solve_ex(sdempc_t* h, const sdempc_solve_args* args);
 
 /* Positional form of sdempc_solve_ex. */
@@ -234,8 +238,8 @@ int sdempc_fetch(sdempc_t* h, const sdempc_solve_args* args);
  * destinations (cudaHostRegister'ed, e.g. every rank's slice of a shared-memory result array in the multi-GPU gather);
  * pageable destinations work but are slower than sdempc_fetch. */
 int sdempc_fetch_direct(sdempc_t* h, const sdempc_solve_args* args);
-/* Page-lock / release a caller-owned host range for sdempc_fetch_direct (cudaHostRegister / cudaHostUnregister on the current
- * device's context; a failure leaves no sticky CUDA error and the caller keeps using sdempc_fetch). */
+/* Page-lock / release a caller-owned host range for sdempc_solve_ex / sdempc_stage / sdempc_fetch_direct (cudaHostRegister /
+ * cudaHostUnregister on the current device's context; a failure leaves no sticky CUDA error and the caller keeps using sdempc_fetch). */
 int sdempc_host_register(void* p, size_t nbytes);
 int sdempc_host_unregister(void* p);
 
